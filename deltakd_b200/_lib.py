@@ -1,0 +1,55 @@
+"""ctypes binding of libdeltakd_sm100.so (C ABI declared in include/deltakd.h).
+
+There is no fallback: if the shared library has not been built, importing this
+module raises, and every compute call on a non-sm_100 device raises
+RuntimeError(dkd_last_error()).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeltakd_sm100.so")
+
+F32, BF16 = 0, 1
+PREC_BF16, PREC_BF16X3 = 0, 1
+OK = 0
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python deltakd_b200/csrc/build.py` "
+        "(deltakd_b200 has no CPU or eager fallback)")
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); tests/test_abi.py checks this table against include/deltakd.h
+SIGNATURES = {
+    "dkd_version": (_i, []),
+    "dkd_last_error": (C.c_char_p, []),
+    "dkd_check_device": (_i, []),
+    "dkd_logit_kd_workspace_bytes": (_sz, [_i64]),
+    "dkd_logit_kd_fwdbwd": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _i, _f, _f, _f, _p, _p, _p, _p, _sz, _p]),
+    "dkd_mask_rank": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "dkd_scale_if_not_one": (_i, [_p, _i64, _i, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return (lib.dkd_last_error() or b"").decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,168 @@
+// Shared device/host helpers for libdeltakd_sm100 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/deltakd.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdeltakd_sm100 is written for sm_100a (B200) only"
+#endif
+
+namespace dkd {
+
+// ---- error plumbing (host) -------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> DKD_E_LAUNCH
+
+#define DKD_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::dkd::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- element access ----------------------------------------------------------
+template <typename T> struct Elt;
+template <> struct Elt<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Elt<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// VEC consecutive elements <-> fp32 registers with one 4/8/16-byte access.
+template <typename T, int VEC> struct Vec {
+  static_assert(VEC == 1 || VEC == 2 || VEC == 4 || VEC == 8, "VEC");
+  static __device__ __forceinline__ void load(const T* p, float (&v)[VEC]) {
+    constexpr int BYTES = VEC * (int)sizeof(T);
+    if constexpr (BYTES == 16) {
+      uint4 r = *reinterpret_cast<const uint4*>(p);
+      unpack<4>(reinterpret_cast<const uint32_t*>(&r), v);
+    } else if constexpr (BYTES == 8) {
+      uint2 r = *reinterpret_cast<const uint2*>(p);
+      unpack<2>(reinterpret_cast<const uint32_t*>(&r), v);
+    } else if constexpr (BYTES == 4) {
+      uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+      unpack<1>(&r, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = Elt<T>::ld(p + i);
+    }
+  }
+  static __device__ __forceinline__ void store(T* p, const float (&v)[VEC]) {
+    constexpr int BYTES = VEC * (int)sizeof(T);
+    if constexpr (BYTES == 16) {
+      uint4 r;
+      pack<4>(v, reinterpret_cast<uint32_t*>(&r));
+      *reinterpret_cast<uint4*>(p) = r;
+    } else if constexpr (BYTES == 8) {
+      uint2 r;
+      pack<2>(v, reinterpret_cast<uint32_t*>(&r));
+      *reinterpret_cast<uint2*>(p) = r;
+    } else if constexpr (BYTES == 4) {
+      uint32_t r;
+      pack<1>(v, &r);
+      *reinterpret_cast<uint32_t*>(p) = r;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) Elt<T>::st(p + i, v[i]);
+    }
+  }
+
+ private:
+  template <int WORDS>
+  static __device__ __forceinline__ void unpack(const uint32_t* w, float (&v)[VEC]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < WORDS; ++i) v[i] = __uint_as_float(w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < WORDS; ++i) {  // bf16 -> fp32 is a 16-bit shift
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+  }
+  template <int WORDS>
+  static __device__ __forceinline__ void pack(const float (&v)[VEC], uint32_t* w) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < WORDS; ++i) w[i] = __float_as_uint(v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < WORDS; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    }
+  }
+};
+
+// ---- reductions ----------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of K values at once; result valid in every thread. `scratch` holds >= K*32 floats.
+template <int K, int THREADS>
+__device__ __forceinline__ void block_sum(float (&v)[K], float* scratch) {
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();  // protect scratch reuse
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[k * WARPS + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) a += scratch[k * WARPS + w];
+    v[k] = a;
+  }
+}
+template <int K, int THREADS>
+__device__ __forceinline__ void block_max(float (&v)[K], float* scratch) {
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_max(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[k * WARPS + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float a = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) a = fmaxf(a, scratch[k * WARPS + w]);
+    v[k] = a;
+  }
+}
+
+}  // namespace dkd

@@ -1,0 +1,314 @@
+// Fused base-CE + soft/hard KD on logits, forward + backward in one sweep.
+// Reference arithmetic: model/loss.py:35 (timm SoftTargetCrossEntropy / LabelSmoothingCrossEntropy,
+// loss.py:244-249), :57-64 (soft KD, note the /numel), :66-67 (hard KD), :241 (mix).
+//
+// One CTA per batch row.  The row of each operand is read from HBM exactly once (held in registers
+// when C <= THREADS*VEC*NV, otherwise re-read through L1/L2), max / log-sum-exp are block-reduced,
+// both gradient rows are written in the same launch, and the last CTA to finish folds the per-row
+// partials in a fixed order (deterministic) into {total, base, kd}.
+// HBM-bound: algorithmic bytes = (reads + grad writes) * B * C * sizeof(elt); no tensor-core work.
+#include "common.cuh"
+
+namespace dkd {
+namespace {
+
+constexpr int kThreads = 128;
+
+struct LogitKdParams {
+  const void* z;      // outputs
+  const void* zk;     // outputs_kd
+  const void* zt;     // teacher logits
+  const void* y;      // soft labels or int64 ids
+  void* gz;
+  void* gzk;
+  float* loss_out;    // [3]
+  float* row_base;    // [B]
+  float* row_kd;      // [B]
+  unsigned int* ticket;
+  int64_t B, C;
+  int label_kind, kd_kind;
+  float smoothing, alpha, tau;
+};
+
+// NV > 0: row cached in registers (C <= kThreads*VEC*NV).  NV == 0: streaming (re-read) path.
+template <typename T, int VEC, int NV>
+__global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
+  __shared__ float scratch[4 * (kThreads / 32)];
+  __shared__ int s_arg[kThreads / 32];
+  __shared__ float s_argv[kThreads / 32];
+  __shared__ bool s_last;
+
+  const int64_t row = blockIdx.x;
+  const int64_t C = p.C;
+  const T* z = p.label_kind >= 0 ? reinterpret_cast<const T*>(p.z) + row * C : nullptr;
+  const T* zk = p.kd_kind ? reinterpret_cast<const T*>(p.zk) + row * C : nullptr;
+  const T* zt = p.kd_kind ? reinterpret_cast<const T*>(p.zt) + row * C : nullptr;
+  const T* y = p.label_kind == 0 ? reinterpret_cast<const T*>(p.y) + row * C : nullptr;
+  const int64_t label = p.label_kind == 1 ? reinterpret_cast<const int64_t*>(p.y)[row] : -1;
+  const float invT = p.kd_kind == 1 ? 1.f / p.tau : 1.f;
+
+  constexpr int NVR = NV > 0 ? NV : 1;
+  float rz[NVR][VEC], rk[NVR][VEC], rt[NVR][VEC], ry[NVR][VEC];
+  const int nchunk = (int)((C + (int64_t)kThreads * VEC - 1) / ((int64_t)kThreads * VEC));
+
+  auto col_of = [&](int it) -> int64_t { return ((int64_t)it * kThreads + threadIdx.x) * VEC; };
+  auto load4 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
+    const int64_t col = col_of(it);
+    if (col < C) {  // C % VEC == 0 by construction
+      if (p.label_kind >= 0) Vec<T, VEC>::load(z + col, a);
+      else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) a[v] = 0.f;
+      }
+      if (p.kd_kind) {
+        Vec<T, VEC>::load(zk + col, b);
+        Vec<T, VEC>::load(zt + col, c);
+      }
+      if (p.label_kind == 0) Vec<T, VEC>::load(y + col, d);
+    }
+  };
+
+  // ---- pass 1: maxima (and teacher argmax for hard KD) -------------------------------------
+  float mx[3] = {-INFINITY, -INFINITY, -INFINITY};  // z, zk*invT, zt*invT
+  float best = -INFINITY;
+  int64_t best_i = INT64_MAX;
+  auto pass1 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC]) {
+    const int64_t col = col_of(it);
+    if (col < C) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        mx[0] = fmaxf(mx[0], a[v]);
+        if (p.kd_kind) {
+          mx[1] = fmaxf(mx[1], b[v] * invT);
+          mx[2] = fmaxf(mx[2], c[v] * invT);
+          if (p.kd_kind == 2 && c[v] > best) { best = c[v]; best_i = col + v; }  // first max within thread
+        }
+      }
+    }
+  };
+  if constexpr (NV > 0) {
+#pragma unroll
+    for (int it = 0; it < NV; ++it) {
+      if (it < nchunk) {
+        load4(it, rz[it], rk[it], rt[it], ry[it]);
+        pass1(it, rz[it], rk[it], rt[it]);
+      }
+    }
+  } else {
+    for (int it = 0; it < nchunk; ++it) {
+      load4(it, rz[0], rk[0], rt[0], ry[0]);
+      pass1(it, rz[0], rk[0], rt[0]);
+    }
+  }
+  block_max<3, kThreads>(mx, scratch);
+  int64_t tgt = label;  // index whose one-hot enters the KD gradient (hard) -- label handled separately
+  int64_t hard_idx = -1;
+  if (p.kd_kind == 2) {
+    // argmax with first-index tie-break: warp shuffle, then across warps
+    float bv = best;
+    long long bi = (long long)best_i;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { s_argv[threadIdx.x >> 5] = bv; s_arg[threadIdx.x >> 5] = (int)bi; }
+    __syncthreads();
+    bv = s_argv[0]; bi = s_arg[0];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w) {
+      if (s_argv[w] > bv || (s_argv[w] == bv && s_arg[w] < bi)) { bv = s_argv[w]; bi = s_arg[w]; }
+    }
+    hard_idx = bi;
+  }
+  (void)tgt;
+
+  // ---- pass 2: sums --------------------------------------------------------------------------
+  // s[0]=sum exp(z-m0)  s[1]=sum exp(a-m1)  s[2]=sum exp(b-m2)  s[3]=sum exp(b-m2)*(b-a)
+  // t[0]=sum y          t[1]=sum y*z (soft labels) | sum z (int labels)   t[2]=z[label]  t[3]=zk[hard_idx]
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, t[4] = {0.f, 0.f, 0.f, 0.f};
+  auto pass2 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
+    const int64_t col = col_of(it);
+    if (col < C) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        s[0] += expf(a[v] - mx[0]);
+        if (p.label_kind == 0) { t[0] += d[v]; t[1] += d[v] * a[v]; }
+        else { t[1] += a[v]; if (col + v == label) t[2] = a[v]; }
+        if (p.kd_kind == 1) {
+          const float av = b[v] * invT, bv = c[v] * invT;
+          const float eb = expf(bv - mx[2]);
+          s[1] += expf(av - mx[1]);
+          s[2] += eb;
+          s[3] += eb * (bv - av);
+        } else if (p.kd_kind == 2) {
+          s[1] += expf(b[v] - mx[1]);
+          if (col + v == hard_idx) t[3] = b[v];
+        }
+      }
+    }
+  };
+  if constexpr (NV > 0) {
+#pragma unroll
+    for (int it = 0; it < NV; ++it) if (it < nchunk) pass2(it, rz[it], rk[it], rt[it], ry[it]);
+  } else {
+    for (int it = 0; it < nchunk; ++it) {
+      load4(it, rz[0], rk[0], rt[0], ry[0]);
+      pass2(it, rz[0], rk[0], rt[0], ry[0]);
+    }
+  }
+  block_sum<4, kThreads>(s, scratch);
+  block_sum<4, kThreads>(t, scratch);
+
+  const float Bf = (float)p.B, Cf = (float)C;
+  const float lse0 = mx[0] + logf(s[0]);
+  float base_row, kd_row = 0.f;
+  if (p.label_kind < 0) base_row = 0.f;
+  else if (p.label_kind == 0) base_row = lse0 * t[0] - t[1];
+  else base_row = (1.f - p.smoothing) * (lse0 - t[2]) + p.smoothing * (lse0 - t[1] / Cf);
+  float lse1 = 0.f, lse2 = 0.f;
+  if (p.kd_kind == 1) {
+    lse1 = mx[1] + logf(s[1]);
+    lse2 = mx[2] + logf(s[2]);
+    kd_row = s[3] / s[2] - lse2 + lse1;  // sum_c p_t (log p_t - log p_s)
+  } else if (p.kd_kind == 2) {
+    lse1 = mx[1] + logf(s[1]);
+    kd_row = lse1 - t[3];
+  }
+
+  // ---- pass 3: gradients -----------------------------------------------------------------------
+  const float wb = (p.kd_kind == 0 ? 1.f : 1.f - p.alpha) / Bf;           // d total / d base_row
+  const float wk = p.kd_kind == 1 ? p.alpha * p.tau / (Bf * Cf) : p.alpha / Bf;
+  const float inv_s0 = 1.f / s[0], inv_s1 = p.kd_kind ? 1.f / s[1] : 0.f, inv_s2 = p.kd_kind == 1 ? 1.f / s[2] : 0.f;
+  T* gz = (p.gz && p.label_kind >= 0) ? reinterpret_cast<T*>(p.gz) + row * C : nullptr;
+  T* gzk = (p.gzk && p.kd_kind) ? reinterpret_cast<T*>(p.gzk) + row * C : nullptr;
+  auto pass3 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
+    const int64_t col = col_of(it);
+    if (col < C) {
+      float g0[VEC], g1[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float sm = expf(a[v] - mx[0]) * inv_s0;
+        if (p.label_kind == 0) g0[v] = (sm * t[0] - d[v]) * wb;
+        else g0[v] = (sm - (col + v == label ? 1.f - p.smoothing : 0.f) - p.smoothing / Cf) * wb;
+        if (p.kd_kind == 1) {
+          const float ps = expf(b[v] * invT - mx[1]) * inv_s1;
+          const float pt = expf(c[v] * invT - mx[2]) * inv_s2;
+          g1[v] = (ps - pt) * wk;
+        } else if (p.kd_kind == 2) {
+          const float ps = expf(b[v] - mx[1]) * inv_s1;
+          g1[v] = (ps - (col + v == hard_idx ? 1.f : 0.f)) * wk;
+        }
+      }
+      if (gz) Vec<T, VEC>::store(gz + col, g0);
+      if (gzk) Vec<T, VEC>::store(gzk + col, g1);
+    }
+  };
+  if (gz || gzk) {
+    if constexpr (NV > 0) {
+#pragma unroll
+      for (int it = 0; it < NV; ++it) if (it < nchunk) pass3(it, rz[it], rk[it], rt[it], ry[it]);
+    } else {
+      for (int it = 0; it < nchunk; ++it) {
+        load4(it, rz[0], rk[0], rt[0], ry[0]);
+        pass3(it, rz[0], rk[0], rt[0], ry[0]);
+      }
+    }
+  }
+
+  // ---- per-row partials; last CTA folds them in a fixed order ----------------------------------
+  if (threadIdx.x == 0) {
+    p.row_base[row] = base_row;
+    p.row_kd[row] = kd_row;
+    __threadfence();
+    const unsigned int done = atomicAdd(p.ticket, 1u);
+    s_last = (done == (unsigned int)(p.B - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float acc[2] = {0.f, 0.f};
+  // fixed thread->row assignment and fixed tree => bit-reproducible
+  for (int64_t r = threadIdx.x; r < p.B; r += kThreads) {
+    acc[0] += __ldcg(p.row_base + r);
+    acc[1] += __ldcg(p.row_kd + r);
+  }
+  block_sum<2, kThreads>(acc, scratch);
+  if (threadIdx.x == 0) {
+    const float base = acc[0] / Bf;  // 0 when label_kind < 0 (KD term only: total = alpha * kd)
+    float kd = 0.f, total = base;
+    if (p.kd_kind == 1) { kd = acc[1] * p.tau * p.tau / (Bf * Cf); total = base * (1.f - p.alpha) + kd * p.alpha; }
+    else if (p.kd_kind == 2) { kd = acc[1] / Bf; total = base * (1.f - p.alpha) + kd * p.alpha; }
+    p.loss_out[0] = total;
+    p.loss_out[1] = base;
+    p.loss_out[2] = kd;
+    *p.ticket = 0u;  // ready for the next call on this workspace
+  }
+}
+
+template <typename T, int VEC>
+int launch_logit_kd(const LogitKdParams& p, cudaStream_t stream) {
+  const int64_t per_chunk = (int64_t)kThreads * VEC;
+  const int64_t nchunk = (p.C + per_chunk - 1) / per_chunk;
+  dim3 grid((unsigned)p.B), block(kThreads);
+  if (nchunk <= 1) logit_kd_kernel<T, VEC, 1><<<grid, block, 0, stream>>>(p);
+  else if (nchunk <= 2) logit_kd_kernel<T, VEC, 2><<<grid, block, 0, stream>>>(p);
+  else if (nchunk <= 4) logit_kd_kernel<T, VEC, 4><<<grid, block, 0, stream>>>(p);
+  else logit_kd_kernel<T, VEC, 0><<<grid, block, 0, stream>>>(p);
+  return check_launch("dkd_logit_kd_fwdbwd");
+}
+
+template <typename T>
+int dispatch_vec(const LogitKdParams& p, cudaStream_t stream) {
+  constexpr int MAXV = 16 / (int)sizeof(T);
+  auto aligned = [&](int vec) {
+    const uintptr_t m = (uintptr_t)vec * sizeof(T) - 1;
+    auto ok = [&](const void* q) { return q == nullptr || (((uintptr_t)q) & m) == 0; };
+    return p.C % vec == 0 && ok(p.z) && ok(p.zk) && ok(p.zt) && (p.label_kind == 1 || ok(p.y)) && ok(p.gz) && ok(p.gzk);
+  };
+  if (aligned(MAXV)) return launch_logit_kd<T, MAXV>(p, stream);
+  if (aligned(MAXV / 2)) return launch_logit_kd<T, MAXV / 2>(p, stream);
+  return launch_logit_kd<T, 1>(p, stream);
+}
+
+}  // namespace
+}  // namespace dkd
+
+extern "C" {
+
+size_t dkd_logit_kd_workspace_bytes(int64_t B) {
+  return (size_t)(B > 0 ? B : 0) * 2 * sizeof(float) + 256;
+}
+
+int dkd_logit_kd_fwdbwd(const void* outputs, const void* outputs_kd, const void* teacher_logits,
+                        const void* labels, int label_kind, int kd_kind, int64_t B, int64_t C, int dtype,
+                        float smoothing, float alpha, float tau, void* g_outputs, void* g_outputs_kd,
+                        float* loss_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream) {
+  using namespace dkd;
+  int rc = dkd_check_device();
+  if (rc != DKD_OK) return rc;
+  DKD_REQUIRE(B > 0 && C > 0 && B < (1ll << 31), DKD_E_SHAPE, "dkd_logit_kd_fwdbwd: bad shape B=%lld C=%lld", (long long)B, (long long)C);
+  DKD_REQUIRE(dtype == DKD_F32 || dtype == DKD_BF16, DKD_E_DTYPE, "dkd_logit_kd_fwdbwd: dtype %d", dtype);
+  DKD_REQUIRE(label_kind >= -1 && label_kind <= 1, DKD_E_UNSUPPORTED, "dkd_logit_kd_fwdbwd: label_kind %d", label_kind);
+  DKD_REQUIRE(kd_kind >= 0 && kd_kind <= 2, DKD_E_UNSUPPORTED, "dkd_logit_kd_fwdbwd: kd_kind %d", kd_kind);
+  DKD_REQUIRE(loss_out && workspace && (label_kind < 0 || (outputs && labels)), DKD_E_SHAPE, "dkd_logit_kd_fwdbwd: null pointer");
+  DKD_REQUIRE(label_kind >= 0 || kd_kind != 0, DKD_E_UNSUPPORTED, "dkd_logit_kd_fwdbwd: nothing to compute (no base term and no KD term)");
+  DKD_REQUIRE(kd_kind == 0 || (outputs_kd && teacher_logits), DKD_E_SHAPE, "dkd_logit_kd_fwdbwd: KD needs outputs_kd and teacher_logits");
+  DKD_REQUIRE(kd_kind != 1 || tau > 0.f, DKD_E_SHAPE, "dkd_logit_kd_fwdbwd: tau must be > 0");
+  DKD_REQUIRE(workspace_bytes >= dkd_logit_kd_workspace_bytes(B), DKD_E_WORKSPACE, "dkd_logit_kd_fwdbwd: workspace too small");
+  DKD_REQUIRE((((uintptr_t)workspace) & 15) == 0, DKD_E_ALIGN, "dkd_logit_kd_fwdbwd: workspace must be 16-byte aligned");
+  LogitKdParams p;
+  p.z = outputs; p.zk = outputs_kd; p.zt = teacher_logits; p.y = labels;
+  p.gz = g_outputs; p.gzk = g_outputs_kd; p.loss_out = loss_out;
+  p.ticket = reinterpret_cast<unsigned int*>(workspace);
+  p.row_base = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  p.row_kd = p.row_base + B;
+  p.B = B; p.C = C; p.label_kind = label_kind; p.kd_kind = kd_kind;
+  p.smoothing = smoothing; p.alpha = alpha; p.tau = tau;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return dtype == DKD_F32 ? dispatch_vec<float>(p, st) : dispatch_vec<__nv_bfloat16>(p, st);
+}
+
+}  // extern "C"

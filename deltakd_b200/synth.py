@@ -16,6 +16,17 @@ TEACHER_TOKENS, TEACHER_DIM = 198, 384
 NUM_LAYERS = 12
 
 
+def default_args(**kw):
+    """Loss-relevant argparse defaults of the reference CLI (tools/train.py:103-136,157-186)."""
+    from types import SimpleNamespace
+    d = dict(lrkd_rank=32, lrkd_alpha=0.1, lrkd_beta=0.1, lrkd_gamma=0.1, saliency_method=1,
+             saliency_mask_ratio=0.5, wasskd_type="l1", mgd_alpha=7e-5, mgd_mask_ratio=0.5,
+             mixup=0.8, cutmix=1.0, cutmix_minmax=None, smoothing=0.1, current_epoch=0,
+             distillation_type="none")
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
 def _gen(seed: int) -> torch.Generator:
     return torch.Generator().manual_seed(seed)
 

@@ -1,0 +1,106 @@
+/*
+ * libdeltakd_sm100 — C ABI of the B200-native DeltaKD distillation-loss hot path.
+ *
+ * The reference (serizard/DeltaKD) has no FFI: its boundary is the Python callable
+ * `DistillationLoss.forward` (model/loss.py:29-242, called at tools/engine.py:48).  Each entry
+ * point below replaces the eager ATen op chain of one piece of that callable; the reference
+ * lines are cited per function.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (inputs const, outputs written, never
+ *    retained past return); the library never allocates or frees;
+ *  - all work is enqueued on `stream`; no host synchronisation, no device->host read-backs;
+ *  - return value: DKD_OK or a negative DKD_E_* code; dkd_last_error() gives the message of the
+ *    last failure on the calling thread; no C++ exception crosses the ABI;
+ *  - `dtype` is the storage type of activations (DKD_F32 / DKD_BF16); accumulation is fp32;
+ *  - scalars losses are fp32 on the device;
+ *  - there is no CPU path: on a device that is not sm_100 every compute call returns DKD_E_ARCH.
+ */
+#ifndef DELTAKD_H_
+#define DELTAKD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DKD_API __attribute__((visibility("default")))
+#else
+#define DKD_API
+#endif
+
+typedef struct CUstream_st* dkd_stream_t; /* == cudaStream_t */
+
+enum { DKD_F32 = 0, DKD_BF16 = 1 };
+
+enum {
+  DKD_OK = 0,
+  DKD_E_SHAPE = -1,
+  DKD_E_DTYPE = -2,
+  DKD_E_ALIGN = -3,
+  DKD_E_ARCH = -4,
+  DKD_E_LAUNCH = -5,
+  DKD_E_WORKSPACE = -6,
+  DKD_E_UNSUPPORTED = -7
+};
+
+/* tensor-core arithmetic of the dense contractions */
+enum {
+  DKD_PREC_BF16 = 0,  /* one bf16 tcgen05 pass, fp32 accumulate                                  */
+  DKD_PREC_BF16X3 = 1 /* hi/lo bf16 split, 3 passes (hi*hi + hi*lo + lo*hi): ~2^-16 relative,   */
+                      /* the mode that meets the fp32 parity gates                              */
+};
+
+DKD_API int dkd_version(void);
+DKD_API const char* dkd_last_error(void);
+/* DKD_OK when the current CUDA device is compute capability 10.x, else DKD_E_ARCH. */
+DKD_API int dkd_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Logit losses: base CE + soft / hard KD, forward and backward in one launch.
+ * Replaces model/loss.py:35 (base criterion: timm SoftTargetCrossEntropy or
+ * LabelSmoothingCrossEntropy, loss.py:244-249), :57-64 (soft KD), :66-67 (hard KD) and the mix
+ * `base*(1-alpha) + kd*alpha` at :241, plus their autograd backward.
+ *
+ *   outputs, outputs_kd, teacher_logits : [B, C] `dtype`, row-major contiguous
+ *                                         (outputs_kd / teacher_logits may be NULL when kd_kind==0)
+ *   labels      : label_kind 0 -> soft targets [B, C] `dtype`; 1 -> int64 class ids [B];
+ *                 -1 -> no base term (outputs/labels/g_outputs ignored; total = alpha * kd)
+ *   kd_kind     : 0 none (loss = base), 1 soft (temperature `tau`), 2 hard (teacher argmax, first max)
+ *   g_outputs, g_outputs_kd : [B, C] `dtype` gradients of the returned loss (NULL -> not written)
+ *   loss_out    : fp32[3] = { total, base, kd }
+ *   workspace   : >= dkd_logit_kd_workspace_bytes(B) bytes, ZERO-INITIALISED ONCE by the caller
+ *                 (holds per-row partials and a ticket counter that the kernel resets itself)
+ */
+DKD_API size_t dkd_logit_kd_workspace_bytes(int64_t B);
+DKD_API int dkd_logit_kd_fwdbwd(const void* outputs, const void* outputs_kd, const void* teacher_logits,
+                        const void* labels, int label_kind, int kd_kind, int64_t B, int64_t C, int dtype,
+                        float smoothing, float alpha, float tau, void* g_outputs, void* g_outputs_kd,
+                        float* loss_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mask selection by rank (bit-exact integer work).  Replaces the double argsort of
+ * model/misc.py:17-30 (random_masking) and :72-81, :118-128, :150-160 (saliency_masking):
+ *   ids_restore[b,i] = rank of score[b,i] in ascending order, ties -> lower index first
+ *   ids_shuffle[b,r] = index of the token with rank r            (NULL -> not written)
+ *   mask[b,i]        = 1.0f if ids_restore[b,i] >= len_keep else 0.0f
+ *   score : fp32 [B, L], L <= 1024.
+ */
+DKD_API int dkd_mask_rank(const float* score, int64_t B, int64_t L, int64_t len_keep, float* mask,
+                  int64_t* ids_restore, int64_t* ids_shuffle, dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * x[i] *= *scale for i < n, skipped entirely (no memory traffic) when *scale == 1.0f.
+ * Used by the autograd backward of the fused fwd+bwd losses: gradients are produced for
+ * d(loss)=1 in the forward sweep and only rescaled when the incoming grad_output is not 1
+ * (e.g. under an AMP GradScaler, tools/engine.py:60).  `scale` is a device fp32 scalar.
+ */
+DKD_API int dkd_scale_if_not_one(void* x, int64_t n, int dtype, const float* scale, dkd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DELTAKD_H_ */

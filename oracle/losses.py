@@ -30,16 +30,14 @@ from oracle.sinkhorn import sinkhorn_divergence
 # --------------------------------------------------------------------------- base CE
 def soft_target_ce(z: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """timm SoftTargetCrossEntropy: mean_b sum_c -y*log_softmax(z) (loss.py:35,247)."""
-    lse = torch.logsumexp(z, dim=-1, keepdim=True)
-    return (-(y * (z - lse)).sum(-1)).mean()
+    return (-(y * F.log_softmax(z, dim=-1)).sum(-1)).mean()
 
 
 def label_smoothing_ce(z: torch.Tensor, labels: torch.Tensor, smoothing: float = 0.1) -> torch.Tensor:
     """timm LabelSmoothingCrossEntropy (loss.py:249): (1-e)*nll + e*mean_c(-logp), batch mean."""
-    lse = torch.logsumexp(z, dim=-1)
-    nll = lse - z.gather(1, labels.view(-1, 1)).squeeze(1)
-    smooth = lse - z.mean(-1)
-    return ((1.0 - smoothing) * nll + smoothing * smooth).mean()
+    logp = F.log_softmax(z, dim=-1)
+    nll = -logp.gather(1, labels.view(-1, 1)).squeeze(1)
+    return ((1.0 - smoothing) * nll + smoothing * (-logp.mean(-1))).mean()
 
 
 def base_criterion_for(args) -> str:
@@ -55,16 +53,15 @@ def base_loss(z, labels, kind: str, smoothing: float = 0.1):
 # --------------------------------------------------------------------------- logit KD
 def soft_kd(z_s: torch.Tensor, z_t: torch.Tensor, T: float) -> torch.Tensor:
     """loss.py:57-64: sum p_t (log p_t - log p_s) * T^2 / numel, p = softmax(z/T)."""
-    lp_s = z_s / T - torch.logsumexp(z_s / T, dim=1, keepdim=True)
-    lp_t = z_t / T - torch.logsumexp(z_t / T, dim=1, keepdim=True)
-    return (lp_t.exp() * (lp_t - lp_s)).sum() * (T * T) / z_s.numel()
+    lp_s = F.log_softmax(z_s / T, dim=1)
+    lp_t = F.log_softmax(z_t / T, dim=1)
+    return F.kl_div(lp_s, lp_t, reduction="sum", log_target=True) * (T * T) / z_s.numel()
 
 
 def hard_kd(z_s: torch.Tensor, z_t: torch.Tensor) -> torch.Tensor:
     """loss.py:66-67: CE(z_s, argmax z_t); argmax = first maximal index."""
     idx = torch.from_numpy(np.argmax(z_t.detach().cpu().numpy(), axis=1)).to(z_s.device)
-    lse = torch.logsumexp(z_s, dim=1)
-    return (lse - z_s.gather(1, idx.view(-1, 1)).squeeze(1)).mean()
+    return F.nll_loss(F.log_softmax(z_s, dim=1), idx)
 
 
 # --------------------------------------------------------------------------- masking
