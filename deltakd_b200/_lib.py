@@ -33,7 +33,9 @@ SIGNATURES = {
     "dkd_logit_kd_workspace_bytes": (_sz, [_i64]),
     "dkd_logit_kd_fwdbwd": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _i, _f, _f, _f, _p, _p, _p, _p, _sz, _p]),
     "dkd_mask_rank": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
-    "dkd_scale_if_not_one": (_i, [_p, _i64, _i, _p, _p]),
+    "dkd_scale_if_not_one": (_i, [_p, _i64, _p, _i64, _i, _p, _p]),
+    "dkd_align_mse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
+    "dkd_align_mse_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1,0 +1,188 @@
+// Persistent, warp-specialised tcgen05 GEMM skeleton for sm_100a:   D[M,N] = sum_k A[M,k] * B[N,k]
+// (both operands K-major bf16, fp32 accumulation in TMEM).
+//
+//   warp 0      : TMA producer (one elected lane) — fills a STAGES-deep ring of {A 128x64, B BNx64} tiles
+//   warp 1      : TMEM allocation + tcgen05.mma issue (one elected lane), tcgen05.commit frees ring slots
+//   warps 2..5  : epilogue — tcgen05.ld of the accumulator (thread = row), policy-defined math and stores
+//
+// TMEM holds ACC accumulator stages of BN fp32 columns so the epilogue of tile i overlaps the MMAs
+// of tile i+1.  The fp32-parity mode ("bf16x3") is expressed by the Loader as extra K iterations
+// over (A plane, B plane) pairs: hi*hi + hi*lo + lo*hi accumulate into the same TMEM tile.
+//
+// Policies:
+//   Loader : Params (tensor maps, extents); num_k_iters(p); issue(p, kit, m_tile, n_tile, sA, sB, bar)
+//   Epi    : Params; State; init(state); tile(p, state, m0, n0, lane_row, tmem_acc); finish(p, state)
+#pragma once
+#include "umma.cuh"
+
+namespace dkd {
+
+template <int BN_, int NI_, int STAGES_, int ACC_>
+struct GemmCfg {
+  static constexpr int BM = 128;       // UMMA M (cta_group::1)
+  static constexpr int BN = BN_;       // tile N
+  static constexpr int NI = NI_;       // MMA instructions per K step (N split)
+  static constexpr int N_INSTR = BN_ / NI_;
+  static constexpr int BK = 64;        // one 128-byte swizzle row of bf16
+  static constexpr int STAGES = STAGES_;
+  static constexpr int ACC = ACC_;
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS_USED = ACC * BN;
+  static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
+  static constexpr int THREADS = 192;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(N_INSTR % 16 == 0 && N_INSTR >= 16 && N_INSTR <= 256, "UMMA N");
+  static_assert(TMEM_COLS_USED <= 512, "TMEM columns");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+template <class Loader, class Epi>
+struct GemmParams {
+  typename Loader::Params ld;
+  typename Epi::Params ep;
+  int m_tiles, n_tiles;
+};
+
+template <class Cfg, class Loader, class Epi>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_constant__ GemmParams<Loader, Epi> p) {
+  using namespace sm100;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* acc_full = bars + 2 * Cfg::STAGES;
+  uint64_t* acc_empty = acc_full + Cfg::ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + Cfg::ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_k = Loader::num_k_iters(p.ld);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < Cfg::ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    fence_barrier_init();
+    Loader::prefetch(p.ld);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        for (int kit = 0; kit < num_k; ++kit) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, Cfg::N_INSTR, MAJOR_K, MAJOR_K);
+      int s = 0; uint32_t ph = 0;
+      int a = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * Cfg::BN);
+        for (int kit = 0; kit < num_k; ++kit) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + (size_t)s * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (size_t)s * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            const uint64_t da = kmajor_desc(a_addr + k * 32);
+#pragma unroll
+            for (int ni = 0; ni < Cfg::NI; ++ni) {
+              const uint64_t db = kmajor_desc(b_addr + ni * Cfg::N_INSTR * 128 + k * 32);
+              umma_bf16(d_tmem + ni * Cfg::N_INSTR, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);                       // ring slot reusable once these MMAs retire
+          if (kit == num_k - 1) umma_commit(&acc_full[a]);  // accumulator complete
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++a == Cfg::ACC) { a = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;  // accumulator row owned by this thread
+    typename Epi::State st;
+    Epi::init(p.ep, st);
+    int a = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Cfg::BN);
+      Epi::tile(p.ep, st, mt * Cfg::BM, nt * Cfg::BN, row_in_tile, t_acc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+      if (++a == Cfg::ACC) { a = 0; aph ^= 1; }
+    }
+    Epi::finish(p.ep, st, threadIdx.x - 64);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loader: plain K-major operands held as bf16 "plane" tensors [planes, rows, K] (3-D tensor maps,
+// box {64, rows_per_box, 1}).  nterms = 1 (bf16) or 3 (bf16x3: planes (0,0), (0,1), (1,0)).
+struct PlaneLoaderParams {
+  CUtensorMap tmA, tmB;
+  int k_blocks;   // ceil(K / 64)
+  int nterms;     // 1 or 3
+};
+template <class Cfg, int B_BOX_ROWS = (Cfg::BN > 256 ? Cfg::BN / 2 : Cfg::BN)>
+struct PlaneLoader {
+  using Params = PlaneLoaderParams;
+  static __device__ __forceinline__ int num_k_iters(const Params& p) { return p.k_blocks * p.nterms; }
+  static __device__ __forceinline__ void prefetch(const Params& p) {
+    sm100::tma_prefetch_desc(&p.tmA);
+    sm100::tma_prefetch_desc(&p.tmB);
+  }
+  static __device__ __forceinline__ void issue(const Params& p, int kit, int mt, int nt, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
+    const int term = kit / p.k_blocks, kb = kit - term * p.k_blocks;
+    const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+    sm100::tma_load_3d(sA, &p.tmA, bar, kb * 64, mt * Cfg::BM, pa);
+#pragma unroll
+    for (int i = 0; i < Cfg::BN / B_BOX_ROWS; ++i)
+      sm100::tma_load_3d(sB + (size_t)i * B_BOX_ROWS * 128, &p.tmB, bar, kb * 64, nt * Cfg::BN + i * B_BOX_ROWS, pb);
+  }
+};
+
+// host helper: 3-D map over bf16 planes [planes][rows][cols] (cols contiguous), box {64, box_rows, 1}
+inline int make_plane_tmap(CUtensorMap* out, const void* base, int64_t planes, int64_t rows, int64_t cols,
+                           int64_t row_stride_elems, int64_t plane_stride_elems, int box_rows, const char* what) {
+  const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)rows, (uint64_t)planes};
+  const uint64_t strides[2] = {(uint64_t)row_stride_elems * 2, (uint64_t)plane_stride_elems * 2};
+  const uint32_t box[3] = {64, (uint32_t)box_rows, 1};
+  return make_tmap_bf16(out, base, 3, dims, strides, box, what);
+}
+
+}  // namespace dkd

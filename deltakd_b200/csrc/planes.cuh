@@ -1,0 +1,18 @@
+// bf16 "plane" operands of the tensor-core contractions.
+// A value x is represented as hi = bf16(x) and, in the bf16x3 mode, lo = bf16(x - hi); products are
+// formed as hi*hi + hi*lo + lo*hi in fp32 TMEM accumulators (relative error ~2^-16).
+// Layout: [P planes][rows][cols] bf16, cols contiguous; plane 0 = hi, plane 1 = lo.
+#pragma once
+#include "common.cuh"
+
+namespace dkd {
+
+// patch tokens of src[B, T, D] (tokens off .. off+n_tok-1) -> dst[P][B*n_tok][D]
+int launch_tokens_to_planes(const void* src, int dtype, int64_t B, int T, int off, int n_tok, int D, int P,
+                            __nv_bfloat16* dst, cudaStream_t st);
+// W[N, K] fp32 -> Wp[P][N][K] (optional) and Wt[P][K][N] (optional)
+int launch_weight_to_planes(const float* W, int N, int K, int P, __nv_bfloat16* Wp, __nv_bfloat16* Wt, cudaStream_t st);
+// ones[2][64][64]: plane 0 has column 0 = 1, everything else 0
+int launch_fill_ones_tile(__nv_bfloat16* ones, cudaStream_t st);
+
+}  // namespace dkd

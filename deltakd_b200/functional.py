@@ -51,15 +51,20 @@ def _workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def _rescale_(g: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
-    """g *= grad_out on the device, skipped when grad_out == 1 (decided on the device)."""
-    if g is None:
-        return None
+def _rescale_(grad_out: torch.Tensor, *grads):
+    """g *= grad_out on the device for every gradient, skipped when grad_out == 1 (decided on the
+    device, no host sync).  Tensors of one dtype are rescaled two per launch."""
     go = grad_out
     if go.dtype != torch.float32 or not go.is_contiguous():
         go = go.to(torch.float32).contiguous()
-    _lib.call("dkd_scale_if_not_one", _ptr(g), g.numel(), _dtype_code(g), _ptr(go), _stream())
-    return g
+    live = [g for g in grads if g is not None and g.numel() > 0]
+    while live:
+        a = live.pop(0)
+        j = next((k for k, g in enumerate(live) if g.dtype == a.dtype), None)
+        b = live.pop(j) if j is not None else None
+        _lib.call("dkd_scale_if_not_one", _ptr(a), a.numel(), _ptr(b), 0 if b is None else b.numel(),
+                  _dtype_code(a), _ptr(go), _stream())
+    return grads
 
 
 # --------------------------------------------------------------------------- logit losses
@@ -87,7 +92,7 @@ class _LogitKD(torch.autograd.Function):
     def backward(ctx, grad_total):
         g0, g1 = ctx.grads
         ctx.grads = None
-        return (_rescale_(g0, grad_total), _rescale_(g1, grad_total)) + (None,) * 8
+        return _rescale_(grad_total, g0, g1) + (None,) * 8
 
 
 def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, smoothing: float = 0.1,
@@ -136,6 +141,109 @@ def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, 
     parts = []
     total = _LogitKD.apply(outputs, outputs_kd, teacher_logits, labels, lk, kk, smoothing, alpha, tau, parts)
     return (total, parts[0]) if return_parts else total
+
+
+# --------------------------------------------------------------------------- precision policy
+_PRECISION = {"mode": None}
+
+
+def set_matmul_precision(mode):
+    """'bf16x3' (hi/lo split, 3 tcgen05 passes, ~2^-16: meets the fp32 parity gates), 'bf16' (one pass),
+    or None = by input dtype (float32 -> bf16x3, bfloat16 -> bf16)."""
+    if mode not in (None, "bf16", "bf16x3"):
+        raise ValueError(mode)
+    _PRECISION["mode"] = mode
+
+
+def _precision_for(t: torch.Tensor) -> int:
+    mode = _PRECISION["mode"]
+    if mode is None:
+        mode = "bf16x3" if t.dtype == torch.float32 else "bf16"
+    return _lib.PREC_BF16X3 if mode == "bf16x3" else _lib.PREC_BF16
+
+
+def _scratch(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
+    """Uninitialised, 1024-byte aligned scratch cached per (device, tag)."""
+    key = (device.index, "scratch:" + tag)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes + 1024:
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    off = (-ws.data_ptr()) % 1024
+    return ws[off:off + nbytes]
+
+
+# --------------------------------------------------------------------------- hidden-state matching
+class _AlignMseLayers(torch.autograd.Function):
+    """sum_i scale * || Linear_i(s_i[:, 1:]) - t_i[:, 2:] ||^2 over the selected layers (fused fwd+bwd)."""
+
+    @staticmethod
+    def forward(ctx, scale, n_layers, s_off, t_off, *tensors):
+        s_list = tensors[:n_layers]
+        t_list = tensors[n_layers:2 * n_layers]
+        w_list = tensors[2 * n_layers:3 * n_layers]
+        b_list = tensors[3 * n_layers:4 * n_layers]
+        dev = s_list[0].device
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        grads = []
+        for i in range(n_layers):
+            s, t, W, b = s_list[i], t_list[i], w_list[i], b_list[i]
+            B, Ts, Ds = s.shape
+            _, Tt, Dt = t.shape
+            n_tok = Ts - s_off
+            dt = _dtype_code(s)
+            prec = _precision_for(s)
+            need_s = ctx.needs_input_grad[4 + i]
+            need_w = ctx.needs_input_grad[4 + 2 * n_layers + i]
+            need_b = b is not None and ctx.needs_input_grad[4 + 3 * n_layers + i]
+            g_s = torch.empty_like(s) if need_s else None
+            g_W = torch.empty_like(W) if (need_w or need_b) else None
+            g_b = torch.empty_like(b) if need_b else None
+            nbytes = _lib.lib.dkd_align_mse_workspace_bytes(B, n_tok, Ds, Dt, prec)
+            ws = _scratch(dev, "align_mse", nbytes)
+            _lib.call("dkd_align_mse_fwdbwd", _ptr(s), _ptr(t), _ptr(W), _ptr(b), B, Ts, s_off, Tt, t_off, n_tok,
+                      Ds, Dt, dt, prec, float(scale), _ptr(g_s), _ptr(g_W), _ptr(g_b), _ptr(loss), _ptr(ws),
+                      ws.numel(), _stream())
+            grads.append((g_s, g_W if need_w else None, g_b))
+        ctx.grads = grads
+        ctx.n_layers = n_layers
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        n = ctx.n_layers
+        grads = ctx.grads
+        ctx.grads = None
+        flat = [g for trip in grads for g in trip]
+        _rescale_(grad_out, *flat)
+        gs = [g[0] for g in grads]
+        gw = [g[1] for g in grads]
+        gb = [g[2] for g in grads]
+        return (None, None, None, None, *gs, *([None] * n), *gw, *gb)
+
+
+def _check_feature_pair(s, t, s_off, t_off):
+    _require_cuda(s, t)
+    if s.dim() != 3 or t.dim() != 3 or s.shape[0] != t.shape[0]:
+        raise ValueError(f"features must be [B, tokens, dim]; got {tuple(s.shape)} and {tuple(t.shape)}")
+    if s.shape[1] - s_off != t.shape[1] - t_off:
+        raise ValueError(f"patch-token counts differ: student {s.shape[1] - s_off} vs teacher {t.shape[1] - t_off}")
+
+
+def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 1, t_off: int = 2):
+    """scale * sum_i sum((linears[i](s_feats[i][:, s_off:]) - t_feats[i][:, t_off:])**2), 0-dim fp32."""
+    n = len(linears)
+    s_list, t_list, w_list, b_list = [], [], [], []
+    for s, t, lin in zip(s_feats, t_feats, linears):
+        _check_feature_pair(s, t, s_off, t_off)
+        t = t.detach()
+        if t.dtype != s.dtype:
+            t = t.to(s.dtype)
+        s_list.append(s.contiguous())
+        t_list.append(t.contiguous())
+        w_list.append(lin.weight.float().contiguous() if lin.weight.dtype != torch.float32 else lin.weight.contiguous())
+        b_list.append(None if lin.bias is None else lin.bias.float().contiguous())
+    return _AlignMseLayers.apply(scale, n, s_off, t_off, *s_list, *t_list, *w_list, *b_list)
 
 
 # --------------------------------------------------------------------------- masking

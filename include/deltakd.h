@@ -93,12 +93,35 @@ DKD_API int dkd_mask_rank(const float* score, int64_t B, int64_t L, int64_t len_
                   int64_t* ids_restore, int64_t* ids_shuffle, dkd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * x[i] *= *scale for i < n, skipped entirely (no memory traffic) when *scale == 1.0f.
+ * x[i] *= *scale for i < n (and x2[i] for i < n2; pass NULL/0 for one tensor), skipped entirely
+ * (no memory traffic) when *scale == 1.0f.
  * Used by the autograd backward of the fused fwd+bwd losses: gradients are produced for
  * d(loss)=1 in the forward sweep and only rescaled when the incoming grad_output is not 1
  * (e.g. under an AMP GradScaler, tools/engine.py:60).  `scale` is a device fp32 scalar.
  */
-DKD_API int dkd_scale_if_not_one(void* x, int64_t n, int dtype, const float* scale, dkd_stream_t stream);
+DKD_API int dkd_scale_if_not_one(void* x, int64_t n, void* x2, int64_t n2, int dtype, const float* scale,
+                                 dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layer-wise hidden-state matching with a linear alignment head, forward + backward:
+ *     y = s[:, s_off:s_off+n_tok, :] W^T + bias ;  d = y - t[:, t_off:t_off+n_tok, :]
+ *     *loss += scale * sum(d^2)                      (accumulates: zero *loss before the first layer)
+ *     g_s = 2*scale * d W  (written into [B,Ts,Ds]; the s_off special-token rows are zeroed)
+ *     g_W = 2*scale * d^T s,   g_b = 2*scale * sum_rows d          (overwritten)
+ * Replaces, per selected layer, `mse_loss(Linear(student[:,1:]), teacher[:,2:], reduction='sum')` and its
+ * backward in curkd_loss early/mid (model/loss.py:376-393; scale = 4e-5/(nL*B)) and the ViTKD
+ * mimicking term (loss.py:277-289; scale = alpha_vitkd/B).
+ *   s [B,Ts,Ds], t [B,Tt,Dt] : `dtype`, contiguous, special tokens included (consumed in place)
+ *   W [Dt,Ds], bias [Dt], g_W, g_b, loss : fp32 ;  g_s : `dtype`  (any g_* may be NULL)
+ *   precision : DKD_PREC_BF16 | DKD_PREC_BF16X3 (tcgen05 bf16 passes, fp32 accumulate in TMEM)
+ *   workspace : >= dkd_align_mse_workspace_bytes(...) bytes, 1024-byte aligned, contents don't matter
+ * Built for the DeiT-Tiny -> DeiT-Small widths: Ds = 192, Dt = 384.
+ */
+DKD_API size_t dkd_align_mse_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
+DKD_API int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const float* bias, int64_t B, int Ts,
+                                 int s_off, int Tt, int t_off, int n_tok, int Ds, int Dt, int dtype, int precision,
+                                 float scale, void* g_s, float* g_W, float* g_b, float* loss, void* workspace,
+                                 size_t workspace_bytes, dkd_stream_t stream);
 
 #ifdef __cplusplus
 }
