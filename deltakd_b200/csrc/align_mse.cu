@@ -11,145 +11,16 @@
 //   4. gemm_tn + StoreRows epilogue   : g_s[:,off:,:] = G W    (rows scattered into [B,Ts,Ds], CLS rows zeroed)
 //   5. gemm_nt (split-K, MN-major)    : g_W += G^T S, g_b += G^T 1 (ones-column trick)
 //   6. fold_partials                  : loss += sum of the per-CTA partials, fixed order (deterministic)
+#include "epilogues.cuh"
 #include "gemm_nt.cuh"
-#include "gemm_tn.cuh"
 #include "planes.cuh"
 
 namespace dkd {
 namespace {
 
-// ---------------------------------------------------------------------------------- epilogues
-struct ResidualMseParams {
-  const void* t;          // teacher [B, Tt, N] (fp32 or bf16), rows b*Tt + t_off + i
-  const float* bias;      // [N] or null
-  __nv_bfloat16* G;       // planes [P][M][N]
-  double* partials;       // [gridDim.x]
-  int64_t M;
-  int N, n_tok, Tt, t_off, planes;
-  float gscale;           // G = gscale * d
-  int t_is_bf16;
-};
-
-template <class Cfg>
-struct ResidualMseEpi {
-  using Params = ResidualMseParams;
-  struct State { float acc; };
-  static __device__ __forceinline__ void init(const Params&, State& st) { st.acc = 0.f; }
-
-  static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc) {
-    const int64_t m = (int64_t)m0 + row_in_tile;
-    const bool live = m < p.M;
-    const int64_t b = live ? m / p.n_tok : 0;
-    const int64_t trow = b * p.Tt + p.t_off + (live ? m - b * p.n_tok : 0);
-#pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
-      float v[32];
-      sm100::tmem_ld32(t_acc + c0, v);
-      float tv[32];
-      if (live) {
-        if (p.t_is_bf16) {
-          const __nv_bfloat16* tp = reinterpret_cast<const __nv_bfloat16*>(p.t) + trow * p.N + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::load(tp + 8 * j, *reinterpret_cast<float(*)[8]>(&tv[8 * j]));
-        } else {
-          const float* tp = reinterpret_cast<const float*>(p.t) + trow * p.N + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) Vec<float, 4>::load(tp + 4 * j, *reinterpret_cast<float(*)[4]>(&tv[4 * j]));
-        }
-      }
-      sm100::tmem_ld_wait();
-      if (live) {
-        float hi[32], lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = v[j] + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f) - tv[j];
-          st.acc = fmaf(d, d, st.acc);
-          const float g = p.gscale * d;
-          hi[j] = g;
-          lo[j] = g - __bfloat162float(__float2bfloat16_rn(g));
-        }
-        __nv_bfloat16* gp = p.G + m * p.N + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(gp + 8 * j, *reinterpret_cast<float(*)[8]>(&hi[8 * j]));
-        if (p.planes == 2) {
-          __nv_bfloat16* gl = gp + p.M * p.N;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(gl + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
-        }
-      }
-    }
-  }
-
-  static __device__ __forceinline__ void finish(const Params& p, State& st, int tid) {
-    __shared__ double s_part[4];
-    double a = (double)st.acc;
-    a = warp_sum(a);
-    if ((tid & 31) == 0) s_part[tid >> 5] = a;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-    if (tid == 0) p.partials[blockIdx.x] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
-  }
-};
-
-struct StoreRowsParams {
-  void* out;              // [B, T_out, N_total] fp32 or bf16; rows b*T_out + off + i
-  int64_t M;
-  int N_total, n_tok, T_out, off;
-  int out_is_bf16;
-};
-
-template <class Cfg>
-struct StoreRowsEpi {
-  using Params = StoreRowsParams;
-  struct State {};
-  static __device__ __forceinline__ void init(const Params&, State&) {}
-  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int n0, int row_in_tile, uint32_t t_acc) {
-    const int64_t m = (int64_t)m0 + row_in_tile;
-    const bool live = m < p.M;
-    const int64_t b = live ? m / p.n_tok : 0;
-    const int64_t i = live ? m - b * p.n_tok : 0;
-    const int64_t orow = b * p.T_out + p.off + i;
-#pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
-      float v[32];
-      sm100::tmem_ld32(t_acc + c0, v);
-      sm100::tmem_ld_wait();
-      if (!live) continue;
-      float z[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) z[j] = 0.f;
-      if (p.out_is_bf16) {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.N_total + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(op + 8 * j, *reinterpret_cast<float(*)[8]>(&v[8 * j]));
-        if (i == 0)  // the special-token rows in front of this sample's patches get zero gradient
-          for (int r = 1; r <= p.off; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(op - (int64_t)r * p.N_total + 8 * j, *reinterpret_cast<float(*)[8]>(&z[8 * j]));
-      } else {
-        float* op = reinterpret_cast<float*>(p.out) + orow * p.N_total + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) Vec<float, 4>::store(op + 4 * j, *reinterpret_cast<float(*)[4]>(&v[4 * j]));
-        if (i == 0)
-          for (int r = 1; r <= p.off; ++r)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) Vec<float, 4>::store(op - (int64_t)r * p.N_total + 4 * j, *reinterpret_cast<float(*)[4]>(&z[4 * j]));
-      }
-    }
-  }
-  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
-};
-
-__global__ void fold_partials_kernel(const double* __restrict__ partials, int n, float scale, float* __restrict__ loss) {
-  // one warp, fixed order: deterministic
-  double a = 0.0;
-  for (int i = threadIdx.x; i < n; i += 32) a += partials[i];
-  a = warp_sum(a);
-  if (threadIdx.x == 0) *loss += (float)(a * (double)scale);
-}
-
 using FwdCfg = GemmCfg<192, 1, 4, 2>;   // Y tile 128 x 192, 4-stage ring, 2 TMEM accumulators
 using DgradCfg = GemmCfg<192, 1, 4, 2>; // g_s tile 128 x 192 (K = 384)
-using WgradCfg = GemmNtCfg<3, true, 1, 4>;  // g_W tile 128(n) x 192(k) + ones column (g_b)
+using WgradCfg = GemmNtCfg<3, true, 208, 0, 4>;  // g_W tile 128(n) x 192(k) + ones column (g_b)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -203,7 +74,7 @@ int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const flo
   const bool want_grads = g_s != nullptr || g_W != nullptr || g_b != nullptr;
 
   // 1-2. operand planes
-  rc = launch_tokens_to_planes(s, dtype, B, Ts, s_off, n_tok, Ds, P, ws.S, st);
+  rc = launch_tokens_to_planes(s, dtype, B, Ts, s_off, n_tok, Ds, P, nullptr, ws.S, st);
   if (rc != DKD_OK) return rc;
   rc = launch_weight_to_planes(W, Dt, Ds, P, ws.Wp, want_grads ? ws.Wt : nullptr, st);
   if (rc != DKD_OK) return rc;
@@ -231,8 +102,7 @@ int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const flo
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
     rc = check_launch("dkd_align_mse_fwdbwd: forward GEMM");
     if (rc != DKD_OK) return rc;
-    fold_partials_kernel<<<1, 32, 0, st>>>(ws.partials, grid, scale, loss);
-    rc = check_launch("dkd_align_mse_fwdbwd: fold");
+    rc = launch_fold_partials(ws.partials, grid, scale, loss, st);
     if (rc != DKD_OK) return rc;
   }
   if (!want_grads) return DKD_OK;
@@ -249,7 +119,7 @@ int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const flo
     if (rc != DKD_OK) return rc;
     p.ld.k_blocks = Dt / 64;
     p.ld.nterms = P == 2 ? 3 : 1;
-    p.ep.out = g_s; p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off;
+    p.ep.out = g_s; p.ep.drop_mask = nullptr; p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off;
     p.ep.out_is_bf16 = dtype == DKD_BF16;
     p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM);
     p.n_tiles = Ds / Cfg::BN;
@@ -264,28 +134,28 @@ int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const flo
   // 5. g_W = G^T S, g_b = G^T 1
   if (g_W || g_b) {
     using Cfg = WgradCfg;
+    using L = NtPlainLoader<Cfg>;
     DKD_REQUIRE(g_W != nullptr, DKD_E_UNSUPPORTED, "dkd_align_mse_fwdbwd: g_b without g_W is not supported");
-    GemmNtParams p;
-    rc = make_plane_tmap(&p.tmA, ws.G, P, M, Dt, Dt, M * Dt, 64, "align_mse G^T");
+    GemmNtParamsT<Cfg, L> p;
+    rc = make_plane_tmap(&p.ld.tmA, ws.G, P, M, Dt, Dt, M * Dt, Cfg::KROWS, "align_mse G^T");
     if (rc != DKD_OK) return rc;
-    rc = make_plane_tmap(&p.tmB, ws.S, P, M, Ds, Ds, M * Ds, 64, "align_mse S (wgrad)");
+    rc = make_plane_tmap(&p.ld.tmB, ws.S, P, M, Ds, Ds, M * Ds, Cfg::KROWS, "align_mse S (wgrad)");
     if (rc != DKD_OK) return rc;
-    rc = make_plane_tmap(&p.tmOnes, ws.ones, 2, 64, 64, 64, 64 * 64, 64, "ones tile");
+    rc = make_plane_tmap(&p.ld.tmOnes, ws.ones, 2, 64, 64, 64, 64 * 64, Cfg::KROWS, "ones tile");
     if (rc != DKD_OK) return rc;
-    launch_fill_ones_tile(ws.ones, st);
+    rc = launch_fill_ones_tile(ws.ones, st);
+    if (rc != DKD_OK) return rc;
     cudaMemsetAsync(g_W, 0, (size_t)Dt * Ds * sizeof(float), st);
     if (g_b) cudaMemsetAsync(g_b, 0, (size_t)Dt * sizeof(float), st);
-    p.D = g_W; p.Dcol = g_b; p.ldd = Ds;
-    p.na_tiles = Dt / 128;
-    p.total_row_blocks = (int)((M + 63) / 64);
-    int splits = max(1, kNumSMs / p.na_tiles);
-    p.row_blocks_per_split = (p.total_row_blocks + splits - 1) / splits;
-    p.splits = (p.total_row_blocks + p.row_blocks_per_split - 1) / p.row_blocks_per_split;
+    p.ep.D = g_W; p.ep.Dcol = g_b; p.ep.ldd = Ds; p.ep.alpha = 1.f;
+    p.ld.ldd = Ds;
+    p.ld.na_tiles = Dt / 128;
+    p.ld.total_row_blocks = (int)((M + Cfg::KROWS - 1) / Cfg::KROWS);
+    nt_make_splits(p.ld.total_row_blocks, kNumSMs / p.ld.na_tiles, &p.ld.splits, &p.ld.row_blocks_per_split);
+    p.ld.b_col0 = 0;
     p.nterms = P == 2 ? 3 : 1;
-    p.b_col0 = 0;
-    p.alpha = 1.f;
-    const int grid = min(kNumSMs, p.na_tiles * p.splits);
-    auto kern = gemm_nt_kernel<Cfg>;
+    const int grid = min(kNumSMs, p.ld.na_tiles * p.ld.splits);
+    auto kern = gemm_nt_kernel<Cfg, L>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
     rc = check_launch("dkd_align_mse_fwdbwd: wgrad GEMM");

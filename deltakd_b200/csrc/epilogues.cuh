@@ -1,0 +1,171 @@
+// Epilogue policies for gemm_tn_kernel (thread = accumulator row; TMEM read in 32-column chunks).
+#pragma once
+#include "gemm_tn.cuh"
+
+namespace dkd {
+
+// fp32 x[32] -> bf16 hi (and lo = x - hi) planes, 64 contiguous bytes each
+__device__ __forceinline__ void store_planes32(__nv_bfloat16* hi_ptr, int64_t plane_stride, int planes, float (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
+  if (planes == 2) {
+    float lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) lo[j] = x[j] - __bfloat162float(__float2bfloat16_rn(x[j]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + plane_stride + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
+  }
+}
+
+// 32 consecutive activations (fp32 or bf16 storage) -> fp32 registers
+__device__ __forceinline__ void load_act32(const void* base, int64_t elem_off, int is_bf16, float (&x)[32]) {
+  if (is_bf16) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + elem_off;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::load(p + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
+  } else {
+    const float* p = reinterpret_cast<const float*>(base) + elem_off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Vec<float, 4>::load(p + 4 * j, *reinterpret_cast<float(*)[4]>(&x[4 * j]));
+  }
+}
+
+// per-CTA fp64 partial of the epilogue threads' fp32 accumulators -> partials[blockIdx.x]
+__device__ __forceinline__ void epilogue_block_partial(float acc, int tid, double* partials) {
+  __shared__ double s_part[4];
+  double a = warp_sum((double)acc);
+  if ((tid & 31) == 0) s_part[tid >> 5] = a;
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
+  if (tid == 0) partials[blockIdx.x] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+}
+
+// *loss += scale * sum(partials[0..n))  — one warp, fixed order (deterministic)
+int launch_fold_partials(const double* partials, int n, float scale, float* loss, cudaStream_t st);
+
+struct ResidualMseParams {
+  const void* t;          // teacher [B, Tt, N] (fp32 or bf16), rows b*Tt + t_off + i
+  const float* bias;      // [N] or null
+  __nv_bfloat16* G;       // planes [P][M][N]
+  double* partials;       // [gridDim.x]
+  int64_t M;
+  int N, n_tok, Tt, t_off, planes;
+  float gscale;           // G = gscale * d
+  int t_is_bf16;
+};
+
+template <class Cfg>
+struct ResidualMseEpi {
+  using Params = ResidualMseParams;
+  struct State { float acc; };
+  static __device__ __forceinline__ void init(const Params&, State& st) { st.acc = 0.f; }
+
+  static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc) {
+    const int64_t m = (int64_t)m0 + row_in_tile;
+    const bool live = m < p.M;
+    const int64_t b = live ? m / p.n_tok : 0;
+    const int64_t trow = b * p.Tt + p.t_off + (live ? m - b * p.n_tok : 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
+      float v[32];
+      sm100::tmem_ld32(t_acc + c0, v);
+      float tv[32];
+      if (live) {
+        if (p.t_is_bf16) {
+          const __nv_bfloat16* tp = reinterpret_cast<const __nv_bfloat16*>(p.t) + trow * p.N + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::load(tp + 8 * j, *reinterpret_cast<float(*)[8]>(&tv[8 * j]));
+        } else {
+          const float* tp = reinterpret_cast<const float*>(p.t) + trow * p.N + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) Vec<float, 4>::load(tp + 4 * j, *reinterpret_cast<float(*)[4]>(&tv[4 * j]));
+        }
+      }
+      sm100::tmem_ld_wait();
+      if (live) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = v[j] + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f) - tv[j];
+          st.acc = fmaf(d, d, st.acc);
+          const float g = p.gscale * d;
+          hi[j] = g;
+          lo[j] = g - __bfloat162float(__float2bfloat16_rn(g));
+        }
+        __nv_bfloat16* gp = p.G + m * p.N + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(gp + 8 * j, *reinterpret_cast<float(*)[8]>(&hi[8 * j]));
+        if (p.planes == 2) {
+          __nv_bfloat16* gl = gp + p.M * p.N;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(gl + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
+        }
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void finish(const Params& p, State& st, int tid) {
+    __shared__ double s_part[4];
+    double a = (double)st.acc;
+    a = warp_sum(a);
+    if ((tid & 31) == 0) s_part[tid >> 5] = a;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    if (tid == 0) p.partials[blockIdx.x] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+  }
+};
+
+struct StoreRowsParams {
+  void* out;              // [B, T_out, N_total] fp32 or bf16; rows b*T_out + off + i
+  const float* drop_mask; // [M] 0/1 or null: rows with mask != 0 are stored as zeros
+  int64_t M;
+  int N_total, n_tok, T_out, off;
+  int out_is_bf16;
+};
+
+template <class Cfg>
+struct StoreRowsEpi {
+  using Params = StoreRowsParams;
+  struct State {};
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int n0, int row_in_tile, uint32_t t_acc) {
+    const int64_t m = (int64_t)m0 + row_in_tile;
+    const bool live = m < p.M;
+    const int64_t b = live ? m / p.n_tok : 0;
+    const int64_t i = live ? m - b * p.n_tok : 0;
+    const int64_t orow = b * p.T_out + p.off + i;
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
+      float v[32];
+      sm100::tmem_ld32(t_acc + c0, v);
+      sm100::tmem_ld_wait();
+      if (!live) continue;
+      if (p.drop_mask != nullptr && __ldg(p.drop_mask + m) != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      float z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0.f;
+      if (p.out_is_bf16) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.N_total + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(op + 8 * j, *reinterpret_cast<float(*)[8]>(&v[8 * j]));
+        if (i == 0)  // the special-token rows in front of this sample's patches get zero gradient
+          for (int r = 1; r <= p.off; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(op - (int64_t)r * p.N_total + 8 * j, *reinterpret_cast<float(*)[8]>(&z[8 * j]));
+      } else {
+        float* op = reinterpret_cast<float*>(p.out) + orow * p.N_total + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Vec<float, 4>::store(op + 4 * j, *reinterpret_cast<float(*)[4]>(&v[4 * j]));
+        if (i == 0)
+          for (int r = 1; r <= p.off; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Vec<float, 4>::store(op - (int64_t)r * p.N_total + 4 * j, *reinterpret_cast<float(*)[4]>(&z[4 * j]));
+      }
+    }
+  }
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+};
+
+
+}  // namespace dkd

@@ -1,29 +1,31 @@
 // Split-K "contract over rows" tcgen05 GEMM for sm_100a:   D[NA, NB] += sum_r A[r, NA] * B[r, NB]
 // (weight gradients and Gram-type products).  Both operands are row-major bf16 plane tensors whose
 // contraction index is the ROW, so they are consumed as MN-major UMMA operands: a TMA box
-// {64 cols, 64 rows} (128-byte swizzle) is one 64(mn) x 64(k) operand block.
+// {64 cols, KROWS rows} (128-byte swizzle) is one 64(mn) x KROWS(k) operand block.
 //
-// Work item = (NA tile of 128 columns, row split).  Each CTA loops over its items; per item it
-// accumulates over the split's rows in TMEM and the epilogue adds the 128 x NB tile into fp32 D with
-// red.global.add (D is zeroed by the host wrapper).  Warp roles as in gemm_tn.cuh.
+// Work item = (output tile, row split); the Loader policy decodes it.  Each CTA loops over its items;
+// per item it accumulates over the split's row blocks in TMEM (one 128 x NB fp32 tile) and the epilogue
+// adds the tile into fp32 D with red.global.add (D is zeroed by the host wrapper).  Warp roles as in
+// gemm_tn.cuh: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
 //
 // The B operand may carry one extra box from a constant "ones" tile (column 0 = 1): its first 16
-// columns extend N by 16 and column NB_DATA of the result is then sum_r A[r, :] (the bias gradient).
+// columns extend N by 16 and column NB_DATA of the result is then sum_r A[r, :] (a bias gradient).
 #pragma once
 #include "umma.cuh"
 
 namespace dkd {
 
-template <int NB_BOXES_, bool ONES_, int NI_, int STAGES_>
+template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64>
 struct GemmNtCfg {
   static constexpr int NA = 128;                      // UMMA M
   static constexpr int NB_BOXES = NB_BOXES_;          // 64-column boxes of B data
   static constexpr bool ONES = ONES_;
   static constexpr int NB_DATA = 64 * NB_BOXES_;
-  static constexpr int NB = NB_DATA + (ONES_ ? 16 : 0);   // MMA N (all instructions together)
-  static constexpr int NI = NI_;
-  static constexpr int N_INSTR = NB / NI_;
-  static constexpr int BOX_BYTES = 64 * 128;          // 64 rows x 128 B
+  static constexpr int NB = NB_DATA + (ONES_ ? 16 : 0);
+  static constexpr int N0 = N0_, N1 = N1_;            // N of the one or two MMA instructions per K step
+  static constexpr int KROWS = KROWS_;                // contraction rows per stage (multiple of 16)
+  static constexpr int KSTEPS = KROWS_ / 16;
+  static constexpr int BOX_BYTES = KROWS_ * 128;
   static constexpr int A_BYTES = 2 * BOX_BYTES;
   static constexpr int B_BYTES = (NB_BOXES_ + (ONES_ ? 1 : 0)) * BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -31,26 +33,31 @@ struct GemmNtCfg {
   static constexpr int TMEM_COLS = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : NB <= 256 ? 256 : 512;
   static constexpr int THREADS = 192;
   static constexpr size_t SMEM = (size_t)STAGES_ * STAGE_BYTES + 1024 + 256;
-  static_assert(N_INSTR % 16 == 0 && N_INSTR <= 256 && (N_INSTR % 64 == 0 || NI_ == 1), "UMMA N split must fall on box boundaries");
+  static_assert(N0_ + N1_ == NB, "instruction N split must cover NB");
+  static_assert(N0_ % 16 == 0 && N0_ <= 256 && N1_ % 16 == 0 && N1_ <= 256 && (N1_ == 0 || N0_ % 64 == 0), "UMMA N split");
+  static_assert(KROWS_ % 16 == 0 && BOX_BYTES % 1024 == 0, "K rows per stage");
   static_assert(NB <= 512 && SMEM <= 227 * 1024, "resources");
 };
 
-struct GemmNtParams {
-  CUtensorMap tmA, tmB, tmOnes;  // 3-D {cols, rows, planes}, box {64, 64, 1}
-  float* D;                      // [NA_total, ldd] fp32, += via red.add
-  float* Dcol;                   // [NA_total] fp32 (+= column NB_DATA), or null
+struct NtEpilogueParams {
+  float* D;      // fp32, += via red.add
+  float* Dcol;   // += column NB_DATA of the tile (ones trick), or null
   int ldd;
-  int na_tiles;                  // NA_total / 128
-  int splits;                    // row splits
-  int row_blocks_per_split;      // 64-row blocks per split
-  int total_row_blocks;
-  int nterms;                    // 1 (bf16) or 3 (bf16x3)
-  int b_col0;                    // first B column (64-aligned)
-  float alpha;                   // scale applied in the epilogue
+  float alpha;
 };
 
-template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_constant__ GemmNtParams p) {
+// Loader policy interface:
+//   Params; num_items(p); decode(p, item, Item&); row_blocks(p, item_info) -> [rb0, rb1);
+//   issue(p, info, term, rb, sA, sB, bar); out_ptr(p, info) -> float* of the tile's (row 0, col 0); col_ptr
+template <class Cfg, class Loader>
+struct GemmNtParamsT {
+  typename Loader::Params ld;
+  NtEpilogueParams ep;
+  int nterms;
+};
+
+template <class Cfg, class Loader>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_constant__ GemmNtParamsT<Cfg, Loader> p) {
   using namespace sm100;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -63,15 +70,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_items = p.na_tiles * p.splits;
+  const int num_items = Loader::num_items(p.ld);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4);
     fence_barrier_init();
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
+    Loader::prefetch(p.ld);
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
@@ -79,33 +85,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto item_range = [&](int item, int& tile, int& rb0, int& rb1) {
-    tile = item % p.na_tiles;
-    const int split = item / p.na_tiles;
-    rb0 = split * p.row_blocks_per_split;
-    rb1 = min(rb0 + p.row_blocks_per_split, p.total_row_blocks);
-  };
-
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tile, rb0, rb1;
-        item_range(item, tile, rb0, rb1);
+        typename Loader::Item it;
+        Loader::decode(p.ld, item, it);
         for (int term = 0; term < p.nterms; ++term) {
-          const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
-          for (int rb = rb0; rb < rb1; ++rb) {
+          for (int rb = it.rb0; rb < it.rb1; ++rb) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-            uint8_t* a = sA + (size_t)s * Cfg::A_BYTES;
-            uint8_t* b = sB + (size_t)s * Cfg::B_BYTES;
-            tma_load_3d(a, &p.tmA, &full[s], tile * 128, rb * 64, pa);
-            tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, &full[s], tile * 128 + 64, rb * 64, pa);
-#pragma unroll
-            for (int i = 0; i < Cfg::NB_BOXES; ++i)
-              tma_load_3d(b + (size_t)i * Cfg::BOX_BYTES, &p.tmB, &full[s], p.b_col0 + i * 64, rb * 64, pb);
-            if constexpr (Cfg::ONES)  // plane 0 of the ones tile is {1,0,0,...}; the lo plane contributes nothing
-              tma_load_3d(b + (size_t)Cfg::NB_BOXES * Cfg::BOX_BYTES, &p.tmOnes, &full[s], 0, 0, pb);
+            mbar_expect_tx(&full[s], Loader::TX_BYTES);
+            Loader::issue(p.ld, it, term, rb, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -113,13 +103,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::N_INSTR, MAJOR_MN, MAJOR_MN);
+      constexpr uint32_t idesc0 = make_idesc_bf16(128, Cfg::N0, MAJOR_MN, MAJOR_MN);
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, Cfg::N1 > 0 ? Cfg::N1 : 16, MAJOR_MN, MAJOR_MN);
       int s = 0; uint32_t ph = 0; uint32_t aph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int tile, rb0, rb1;
-        item_range(item, tile, rb0, rb1);
-        const int nk = (rb1 - rb0) * p.nterms;
-        if (nk <= 0) continue;  // (the host never creates empty splits)
+        typename Loader::Item it;
+        Loader::decode(p.ld, item, it);
+        const int nk = (it.rb1 - it.rb0) * p.nterms;
+        if (nk <= 0) continue;  // (hosts never create empty splits)
         mbar_wait(acc_empty, aph ^ 1);
         tc_fence_after();
         for (int kit = 0; kit < nk; ++kit) {
@@ -128,13 +119,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           const uint32_t a_addr = smem_u32(sA + (size_t)s * Cfg::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)s * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 64 rows = 4 x UMMA_K; 16 k-rows = 2 groups of 8 rows = 2048 B
+          for (int k = 0; k < Cfg::KSTEPS; ++k) {  // UMMA_K = 16 rows = 2 groups of 8 rows = 2048 B
             const uint64_t da = mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
-#pragma unroll
-            for (int ni = 0; ni < Cfg::NI; ++ni) {
-              const uint64_t db = mnmajor_desc(b_addr + ni * (Cfg::N_INSTR / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES);
-              umma_bf16(tmem_base + ni * Cfg::N_INSTR, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
-            }
+            umma_bf16(tmem_base, da, mnmajor_desc(b_addr + k * 2048, Cfg::BOX_BYTES), idesc0, (kit | k) != 0 ? 1u : 0u);
+            if constexpr (Cfg::N1 > 0)
+              umma_bf16(tmem_base + Cfg::N0, da, mnmajor_desc(b_addr + (Cfg::N0 / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES),
+                        idesc1, (kit | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);
           if (kit == nk - 1) umma_commit(acc_full);
@@ -148,28 +138,26 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
     const int row = quad * 32 + lane;
     uint32_t aph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int tile, rb0, rb1;
-      item_range(item, tile, rb0, rb1);
-      if (rb1 <= rb0) continue;
-      {
-        mbar_wait(acc_full, aph);
-        tc_fence_after();
-        const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16);
-        float* drow = p.D + (size_t)(tile * 128 + row) * p.ldd;
+      typename Loader::Item it;
+      Loader::decode(p.ld, item, it);
+      if (it.rb1 <= it.rb0) continue;
+      mbar_wait(acc_full, aph);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16);
+      float* drow = p.ep.D + it.d_off + (size_t)row * p.ep.ldd;
 #pragma unroll 1
-        for (int c0 = 0; c0 < Cfg::NB_DATA; c0 += 32) {
-          float v[32];
-          tmem_ld32(t_acc + c0, v);
-          tmem_ld_wait();
+      for (int c0 = 0; c0 < Cfg::NB_DATA; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_acc + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j] * p.alpha);
-        }
-        if constexpr (Cfg::ONES) {
-          float v[32];
-          tmem_ld32(t_acc + Cfg::NB_DATA - 16, v);  // columns NB_DATA-16 .. NB_DATA+15 (stay inside the allocation)
-          tmem_ld_wait();
-          if (p.Dcol) atomicAdd(p.Dcol + tile * 128 + row, v[16] * p.alpha);
-        }
+        for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j] * p.ep.alpha);
+      }
+      if constexpr (Cfg::ONES) {
+        float v[32];
+        tmem_ld32(t_acc + Cfg::NB_DATA - 16, v);  // columns NB_DATA-16 .. NB_DATA+15 (inside the allocation)
+        tmem_ld_wait();
+        if (p.ep.Dcol && it.dcol_off >= 0) atomicAdd(p.ep.Dcol + it.dcol_off + row, v[16] * p.ep.alpha);
       }
       tc_fence_before();
       __syncwarp();
@@ -184,6 +172,60 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+struct NtItem {
+  int rb0, rb1;      // row blocks [rb0, rb1) of KROWS rows
+  int a_col0;        // first A column (output row) of the tile
+  int b_col0;        // first B column
+  int64_t d_off;     // element offset of the tile's (0,0) in D
+  int dcol_off;      // offset into Dcol, or -1
+  int aux;           // loader specific (e.g. filter tap)
+};
+
+// Plain loader: A = planes [P][R][NA_total], B = planes [P][R][NB_total], 3-D maps {cols, rows, planes}, box {64, KROWS, 1}.
+struct NtPlainParams {
+  CUtensorMap tmA, tmB, tmOnes;
+  int na_tiles, splits, row_blocks_per_split, total_row_blocks, b_col0, ldd;
+};
+template <class Cfg>
+struct NtPlainLoader {
+  using Params = NtPlainParams;
+  using Item = NtItem;
+  static constexpr uint32_t TX_BYTES = Cfg::STAGE_BYTES;
+  static __device__ __forceinline__ int num_items(const Params& p) { return p.na_tiles * p.splits; }
+  static __device__ __forceinline__ void prefetch(const Params& p) {
+    sm100::tma_prefetch_desc(&p.tmA);
+    sm100::tma_prefetch_desc(&p.tmB);
+  }
+  static __device__ __forceinline__ void decode(const Params& p, int item, Item& it) {
+    const int tile = item % p.na_tiles, split = item / p.na_tiles;
+    it.rb0 = split * p.row_blocks_per_split;
+    it.rb1 = min(it.rb0 + p.row_blocks_per_split, p.total_row_blocks);
+    it.a_col0 = tile * 128;
+    it.b_col0 = p.b_col0;
+    it.d_off = (int64_t)tile * 128 * p.ldd;
+    it.dcol_off = tile * 128;
+    it.aux = 0;
+  }
+  static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+    sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
+    sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
+#pragma unroll
+    for (int i = 0; i < Cfg::NB_BOXES; ++i)
+      sm100::tma_load_3d(b + (size_t)i * Cfg::BOX_BYTES, &p.tmB, bar, it.b_col0 + i * 64, rb * Cfg::KROWS, pb);
+    if constexpr (Cfg::ONES)  // plane 0 of the ones tile is {1,0,0,...}; its lo plane is all zero
+      sm100::tma_load_3d(b + (size_t)Cfg::NB_BOXES * Cfg::BOX_BYTES, &p.tmOnes, bar, 0, 0, pb);
+  }
+};
+
+// host: split `total_row_blocks` over about `want` splits with no empty split
+inline void nt_make_splits(int total_row_blocks, int want, int* splits, int* per_split) {
+  if (want < 1) want = 1;
+  *per_split = (total_row_blocks + want - 1) / want;
+  if (*per_split < 1) *per_split = 1;
+  *splits = (total_row_blocks + *per_split - 1) / *per_split;
 }
 
 }  // namespace dkd

@@ -17,9 +17,10 @@
 
 namespace dkd {
 
-template <int BN_, int NI_, int STAGES_, int ACC_>
+template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128>
 struct GemmCfg {
   static constexpr int BM = 128;       // UMMA M (cta_group::1)
+  static constexpr int TILE_M = TILE_M_;  // rows of the tile that carry data (126 = 9 image rows for the conv loader)
   static constexpr int BN = BN_;       // tile N
   static constexpr int NI = NI_;       // MMA instructions per K step (N split)
   static constexpr int N_INSTR = BN_ / NI_;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         for (int kit = 0; kit < num_k; ++kit) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full[s], Loader::TX_BYTES);
           Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Cfg::BN);
-      Epi::tile(p.ep, st, mt * Cfg::BM, nt * Cfg::BN, row_in_tile, t_acc);
+      Epi::tile(p.ep, st, mt * Cfg::TILE_M, nt * Cfg::BN, row_in_tile, t_acc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -161,6 +162,7 @@ struct PlaneLoaderParams {
 template <class Cfg, int B_BOX_ROWS = (Cfg::BN > 256 ? Cfg::BN / 2 : Cfg::BN)>
 struct PlaneLoader {
   using Params = PlaneLoaderParams;
+  static constexpr uint32_t TX_BYTES = Cfg::STAGE_BYTES;
   static __device__ __forceinline__ int num_k_iters(const Params& p) { return p.k_blocks * p.nterms; }
   static __device__ __forceinline__ void prefetch(const Params& p) {
     sm100::tma_prefetch_desc(&p.tmA);

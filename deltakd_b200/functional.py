@@ -246,6 +246,62 @@ def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 
     return _AlignMseLayers.apply(scale, n, s_off, t_off, *s_list, *t_list, *w_list, *b_list)
 
 
+# --------------------------------------------------------------------------- masked generation (MGD family)
+class _MaskedGeneration(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scale, s_off, t_off, t, mask, s, Wa, ba, mask_token, c1w, c1b, c2w, c2b):
+        B, Ts, Ds = s.shape
+        _, Tt, Dt = t.shape
+        dev = s.device
+        prec = _precision_for(s)
+        need = ctx.needs_input_grad[5:]
+        g_s = torch.empty_like(s) if need[0] else None
+        outs = [g_s]
+        for flag, ref in zip(need[1:], (Wa, ba, mask_token, c1w, c1b, c2w, c2b)):
+            outs.append(torch.empty_like(ref) if (flag and ref is not None) else None)
+        # weight gradients come together with their bias gradient's GEMM inputs; nothing else to couple
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        nbytes = _lib.lib.dkd_masked_generation_workspace_bytes(B, Ts - s_off, Ds, Dt, prec)
+        ws = _scratch(dev, "mgd", nbytes)
+        _lib.call("dkd_masked_generation_fwdbwd", _ptr(s), _ptr(t), _ptr(mask), _ptr(Wa), _ptr(ba), _ptr(mask_token),
+                  _ptr(c1w), _ptr(c1b), _ptr(c2w), _ptr(c2b), B, Ts, s_off, Tt, t_off, Ds, Dt, _dtype_code(s), prec,
+                  float(scale), *[_ptr(o) for o in outs], _ptr(loss), _ptr(ws), ws.numel(), _stream())
+        ctx.grads = outs
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        outs = ctx.grads
+        ctx.grads = None
+        _rescale_(grad_out, *outs)
+        return (None, None, None, None, None, *outs)
+
+
+def masked_generation_loss(s_feat, t_feat, align, mask_token, generation, *, scale: float, mask=None,
+                           mask_ratio=None, noise=None, s_off: int = 1, t_off: int = 2):
+    """scale * sum(mask * (generation(where(mask, mask_token, align(s[:, s_off:]))) - t[:, t_off:])**2).
+
+    `mask` [B,196] (1 = masked) is used if given; otherwise it is drawn like the reference's
+    random_masking: noise = torch.rand(B, 196, device) (misc.py:14) -> rank -> mask (dkd_mask_rank)."""
+    _check_feature_pair(s_feat, t_feat, s_off, t_off)
+    B = s_feat.shape[0]
+    L = s_feat.shape[1] - s_off
+    if mask is None:
+        if noise is None:
+            noise = torch.rand(B, L, device=s_feat.device)
+        len_keep = int(L * (1 - mask_ratio))
+        mask, _, _ = mask_rank(noise, len_keep, want_shuffle=False)
+    mask = mask.detach().to(torch.float32).contiguous()
+    conv1, conv2 = generation[0], generation[2]
+    t = t_feat.detach()
+    if t.dtype != s_feat.dtype:
+        t = t.to(s_feat.dtype)
+    f32 = lambda x: None if x is None else (x if x.dtype == torch.float32 else x.float()).contiguous()
+    return _MaskedGeneration.apply(scale, s_off, t_off, t.contiguous(), mask, s_feat.contiguous(), f32(align.weight),
+                                   f32(align.bias), f32(mask_token.reshape(-1)), f32(conv1.weight), f32(conv1.bias),
+                                   f32(conv2.weight), f32(conv2.bias))
+
+
 # --------------------------------------------------------------------------- masking
 def mask_rank(score: torch.Tensor, len_keep: int, want_shuffle: bool = True):
     """(mask fp32 [B,L], ids_restore int64 [B,L], ids_shuffle int64 [B,L] | None) from fp32 scores."""

@@ -123,6 +123,28 @@ DKD_API int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, c
                                  float scale, void* g_s, float* g_W, float* g_b, float* loss, void* workspace,
                                  size_t workspace_bytes, dkd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Masked generative distillation core, forward + backward (14x14 token grid, Ds = 192, Dt = 384):
+ *     x   = s[:, s_off:, :] W_align^T + b_align
+ *     x_m = where(mask, mask_token, x)
+ *     g   = conv3x3(relu(conv3x3(x_m; conv1)); conv2)          (pad 1, NHWC = the token layout)
+ *     *loss += scale * sum( mask * (g - t[:, t_off:, :])^2 )   (accumulates)
+ * plus the gradients of every input that has a non-NULL g_* pointer (all overwritten).
+ * Replaces mgd_loss (model/loss.py:422-451; scale = mgd_alpha/(B*196*Dt)), saliency_mgd_loss (:335-360;
+ * scale = 4/(B*196*Dt)), the late phase of curkd_loss (:394-420; scale = 5e-5/B) and the ViTKD
+ * generation term (:291-310), including `student.generation` = Conv2d-ReLU-Conv2d (models.py:148-151).
+ *   mask : fp32 [B, 196], 1 = masked (from dkd_mask_rank) ;  mask_token : fp32 [Dt]
+ *   conv*_w : fp32 [Dt, Dt, 3, 3] (PyTorch layout), conv*_b : fp32 [Dt]
+ */
+DKD_API size_t dkd_masked_generation_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
+DKD_API int dkd_masked_generation_fwdbwd(const void* s, const void* t, const float* mask, const float* W_align,
+                                         const float* b_align, const float* mask_token, const float* conv1_w,
+                                         const float* conv1_b, const float* conv2_w, const float* conv2_b, int64_t B,
+                                         int Ts, int s_off, int Tt, int t_off, int Ds, int Dt, int dtype, int precision,
+                                         float scale, void* g_s, float* g_W_align, float* g_b_align, float* g_mask_token,
+                                         float* g_conv1_w, float* g_conv1_b, float* g_conv2_w, float* g_conv2_b,
+                                         float* loss, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

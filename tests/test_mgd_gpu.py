@@ -1,0 +1,94 @@
+"""GPU: masked generative distillation family (MGD, CurKD late phase) — tcgen05 implicit-GEMM convolutions
+vs the oracle and the reference goldens.  The reference draws its mask noise with torch.rand on the CPU; the
+tests inject that same noise tensor so that mask selection is bit-identical."""
+from unittest import mock
+
+import pytest
+import torch
+
+from oracle import losses as O
+from oracle.util import digest, rel_err
+from tests.cases import build_case
+from deltakd_b200 import heads as H
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _run(c):
+    from deltakd_b200 import DistillationLoss, call_base_loss
+    crit = DistillationLoss(call_base_loss(c.args), c.teacher, c.kind, c.alpha, c.tau)
+    noise = c.noise
+    with mock.patch("torch.rand", side_effect=lambda *a, **k: noise.clone()):
+        loss = crit(torch.zeros(c.B, 3, 2, 2, device="cuda"), c.outputs, c.student, c.s_feats, c.labels, c.args)
+    loss.backward()
+    return loss
+
+
+@pytest.mark.parametrize("name", ["mgd_r05", "mgd_r03", "curkd_ep200"])
+def test_masked_generation_matches_reference(golden, name):
+    c = build_case(name, device="cuda")
+    loss = _run(c)
+    heads = H.head_tensors(c.student)
+    for tag in ("f32", "f64"):
+        ref = float(golden[f"{name}/{tag}/loss"])
+        assert abs(loss.item() - ref) <= LOSS_RTOL * abs(ref), (tag, loss.item(), ref)
+    o = build_case(name, dtype=torch.float64)
+    oh = H.head_tensors(o.student)
+    ol = O.distillation_loss(o.kind, o.outputs, o.labels, o.teacher_logits, o.s_feats, o.t_feats, oh, o.args,
+                             o.alpha, o.tau, noise=o.noise)
+    ol.backward()
+    assert abs(loss.item() - ol.item()) <= LOSS_RTOL * abs(ol.item())
+    for i, (f, g) in enumerate(zip(c.s_feats, o.s_feats)):
+        if g.grad is not None and float(g.grad.abs().sum()) > 0:
+            assert rel_err(f.grad, g.grad) < GRAD_RTOL, f"g_sfeat{i}"
+            assert float(f.grad[:, 0].abs().max()) == 0.0
+    checked = 0
+    for k in oh:
+        if oh[k].grad is not None and float(oh[k].grad.abs().sum()) > 0:
+            assert heads[k].grad is not None, k
+            assert rel_err(heads[k].grad, oh[k].grad) < GRAD_RTOL, k
+            checked += 1
+    assert checked >= 7  # align w/b, mask_token, 2 x (conv w, b)
+    for tag in ("f32", "f64"):
+        for k, p in heads.items():
+            key = f"{name}/{tag}/g_head/{k}"
+            if key in golden.files and p.grad is not None:
+                assert rel_err(digest(p.grad), golden[key]) < GRAD_RTOL, key
+
+
+@pytest.mark.parametrize("B,ratio", [(1, 0.5), (5, 0.25), (9, 0.9)])
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_generation_shapes_and_modes(B, ratio, mode):
+    """tile tails (B*14 image rows not a multiple of 9 / 8), mask ratios, both precisions (stated tolerances)."""
+    from deltakd_b200 import functional as Fn
+    from deltakd_b200 import synth
+    from types import SimpleNamespace
+    Fn.set_matmul_precision(mode)
+    try:
+        args = SimpleNamespace(distillation_type="mgd")
+        teacher, student = synth.FeatureReplayModel(384), synth.FeatureReplayModel(192)
+        torch.manual_seed(1)
+        H.attach_distillation_heads(student, teacher, args)
+        with torch.no_grad():
+            student.mask_token.normal_(0, 0.1)
+        s_feats, t_feats = synth.make_features(B, 3, layers=[11])
+        noise = synth.make_noise(B, seed=B)
+        heads64 = {k: v.detach().double().requires_grad_(True) for k, v in H.head_tensors(student).items()}
+        s64 = s_feats[11].double().requires_grad_(True)
+        ref = O.mgd([s64], [t_feats[11].double()], heads64, 7e-5, ratio, noise)
+        ref.backward()
+        student = student.cuda()
+        sc = s_feats[11].cuda().requires_grad_(True)
+        loss = Fn.masked_generation_loss(sc, t_feats[11].cuda(), student.align, student.mask_token, student.generation,
+                                         mask_ratio=ratio, noise=noise.cuda(), scale=7e-5 / (B * 196 * 384))
+        loss.backward()
+        lt, gt = (1e-5, 1e-4) if mode == "bf16x3" else (5e-3, 3e-2)   # one bf16 pass through two K=3456 convolutions
+        assert abs(loss.item() - ref.item()) <= lt * abs(ref.item()), (loss.item(), ref.item())
+        assert rel_err(sc.grad, s64.grad) < gt
+        for k, p in H.head_tensors(student).items():
+            assert rel_err(p.grad, heads64[k].grad) < gt, k
+    finally:
+        Fn.set_matmul_precision(None)
