@@ -149,32 +149,37 @@ def curkd_hidden(s_feats, t_feats, heads, epoch: int) -> torch.Tensor:
     return total / float(len(layers)) / B * 4e-5
 
 
-def generator(x_tokens: torch.Tensor, heads: dict) -> torch.Tensor:
+def generator(x_tokens: torch.Tensor, heads: dict, probe: dict | None = None) -> torch.Tensor:
     """student.generation = Conv3x3 -> ReLU -> Conv3x3 on the hw x hw token grid (models.py:148-151);
-    the [B,N,D] token layout is NHWC, the reference permutes to NCHW (loss.py:444-446)."""
+    the [B,N,D] token layout is NHWC, the reference permutes to NCHW (loss.py:444-446).
+    `probe` (tests only): probe["pre"] receives the ReLU pre-activations [B,D,hw,hw]; if probe["gate"] is
+    set it replaces the ReLU's own 0/1 gate (used to study gate flips of near-zero pre-activations)."""
     B, N, D = x_tokens.shape
     hw = int(N ** 0.5)
     img = x_tokens.reshape(B, hw, hw, D).permute(0, 3, 1, 2)
-    h = F.relu(F.conv2d(img, heads["generation.0.weight"], heads["generation.0.bias"], padding=1))
+    pre = F.conv2d(img, heads["generation.0.weight"], heads["generation.0.bias"], padding=1)
+    if probe is not None:
+        probe["pre"] = pre.detach()
+    h = pre * probe["gate"] if (probe is not None and probe.get("gate") is not None) else F.relu(pre)
     g = F.conv2d(h, heads["generation.2.weight"], heads["generation.2.bias"], padding=1)
     return g.flatten(2).transpose(1, 2)
 
 
-def masked_generation_sse(x_aligned, mask, t_patch, heads) -> torch.Tensor:
+def masked_generation_sse(x_aligned, mask, t_patch, heads, probe=None) -> torch.Tensor:
     """Shared core of mgd / saliency_mgd / curkd-late / vitkd-gen:
     where(mask, mask_token, x) -> generator -> sum m*(g - t)^2 (loss.py:436-450 et al.)."""
     m = mask.unsqueeze(-1).to(x_aligned.dtype)
     x_m = x_aligned * (1 - m) + heads["mask_token"].reshape(1, 1, -1) * m
-    g = generator(x_m, heads)
+    g = generator(x_m, heads, probe)
     return (m * (g - t_patch) ** 2).sum()
 
 
-def mgd(s_feats, t_feats, heads, mgd_alpha: float, mask_ratio: float, noise) -> torch.Tensor:
+def mgd(s_feats, t_feats, heads, mgd_alpha: float, mask_ratio: float, noise, probe=None) -> torch.Tensor:
     """mgd_loss (loss.py:422-451): mean over B*N*D, times mgd_alpha."""
     x = _align(s_feats[-1], heads["align.weight"], heads["align.bias"])
     _, mask, _, _ = random_masking(x, mask_ratio, noise)
     t = t_feats[-1][:, 2:]
-    return masked_generation_sse(x, mask, t, heads) / t.numel() * mgd_alpha
+    return masked_generation_sse(x, mask, t, heads, probe) / t.numel() * mgd_alpha
 
 
 def saliency_mgd(s_feats, t_feats, heads, mask_ratio: float, method: int) -> torch.Tensor:
