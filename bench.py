@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py โ DeltaKD distillation-loss hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference] [--no-extras]
 
 A "step" is one pass of the hot path (loss forward + backward through
 `deltakd_b200.DistillationLoss`) over one batch of synthetic teacher/student outputs.
@@ -11,10 +11,12 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md ย
                CUDA graph (no Python between launches); input sets rotate through > L2-size data
   e2e          same metric through the public API with HOST (pinned) inputs: per step H2D of the
                step's tensors, criterion(...) + backward, D2H read of the loss
-  roofline     dominant kernel: algorithmic bytes (or flops) per launch / its mean duration,
-               measured with CUDA events around that kernel's launches in a separate timed loop
+  roofline     the fused loss op's kernels alone (the C-ABI call, replayed from a CUDA graph and timed
+               with CUDA events): algorithmic bytes (or flops) per call / mean call duration
   cpu_baseline the CPU oracle (restatement of the reference's PyTorch loss, `kind: "port"`) timed on
                this box's host cores on a bounded sample of the same workload
+  workloads    the other BASELINE.json configs (feature losses at their full batch sizes), each with
+               value / e2e / roofline / cpu_baseline, measured the same way (skipped by --no-extras)
   --impl reference : the reference arm = the same CPU oracle with all host threads (the reference is
                pure PyTorch; /root/reference does not exist on the GPU box)
 """
@@ -35,6 +37,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 L2_BYTES = 126 * 1024 * 1024
+METRIC = "distill-loss fwd+bwd samples/s"
 
 
 def peaks():
@@ -42,7 +45,7 @@ def peaks():
     if os.path.exists(path):
         d = json.load(open(path))
         return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback (B200_PROFILING.md)")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -67,12 +70,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.time(), line.strip()))
 
-    def stop(self, t0: float, t1: float):
+    def stop(self, windows):
+        """windows: list of (t0, t1) wall-clock intervals of the timed regions."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [s for t, s in self.samples if t0 - 0.05 <= t <= t1 + 0.15] or [s for _, s in self.samples[-3:]]
+        rows = [s for t, s in self.samples if any(t0 - 0.05 <= t <= t1 + 0.15 for t0, t1 in windows)]
+        rows = rows or [s for _, s in self.samples[-3:]]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -95,16 +100,23 @@ def _pin(t):
 
 # ----------------------------------------------------------------------------- workloads
 class Workload:
-    """One BASELINE.json config: builds device inputs, the step, its algorithmic cost and the CPU oracle."""
+    """One BASELINE.json config: builds inputs, the step, its algorithmic cost and the CPU oracle step."""
     name = ""
     dtype = "f32"
+    B = 0
+    bound = "hbm"
+    cpu_B = None          # batch of the bounded CPU sample (None -> same as B)
+    default_steps = 20
 
     def __init__(self, device, rank):
         self.device, self.rank = device, rank
 
-    # number of rotating input sets so the working set exceeds L2
     def nsets(self):
-        return max(2, int(1.5 * L2_BYTES / max(1, self.bytes_per_set())) + 1)
+        """Rotating input sets so that the working set between reuses exceeds L2."""
+        return max(1, int(1.5 * L2_BYTES / max(1, self.bytes_per_set())) + 1) if self.bytes_per_set() < 2 * L2_BYTES else 1
+
+    def algorithmic_flops(self):
+        return 0.0
 
 
 class LogitKD(Workload):
@@ -113,8 +125,8 @@ class LogitKD(Workload):
     dtype = "bf16"
     B, C, kind, alpha, tau = 256, 1000, "soft", 0.1, 3.0
     tdtype = torch.bfloat16
-    launches_per_step = 3   # fused fwd+bwd kernel + 2 conditional-rescale kernels in backward
     dominant = "logit_kd_kernel"
+    default_steps = 200
 
     def bytes_per_set(self):
         return 4 * self.B * self.C * self.tdtype.itemsize
@@ -122,18 +134,18 @@ class LogitKD(Workload):
     def algorithmic_bytes(self):  # 4 reads + 2 gradient writes (SURVEY ยง8d cfg2: 6*B*C*elt)
         return 6 * self.B * self.C * self.tdtype.itemsize
 
-    def host_sets(self, n):
+    def host_sets(self, n, B=None):
         from deltakd_b200 import synth
+        B = B or self.B
         sets = []
         for i in range(n):
-            z, zk, zt, y = synth.make_logits(self.B, self.C, 1234 + self.rank + 17 * i)
+            z, zk, zt, y = synth.make_logits(B, self.C, 1234 + self.rank + 17 * i)
             sets.append(tuple(_pin(t.to(self.tdtype)) for t in (z, zk, zt, y)))
         return sets
 
     def setup(self):
         from deltakd_b200 import DistillationLoss, call_base_loss, synth
-        from deltakd_b200.synth import default_args
-        self.args = default_args()
+        self.args = synth.default_args()
         self.teacher = synth.FeatureReplayModel(384)
         self.crit = DistillationLoss(call_base_loss(self.args), self.teacher, self.kind, self.alpha, self.tau)
         self.inputs = torch.zeros(self.B, 3, 2, 2, device=self.device)  # images feed only the (replayed) teacher
@@ -153,84 +165,336 @@ class LogitKD(Workload):
         loss.backward()
         return loss
 
-    def kernel_only(self, ds):
-        """Launch just the dominant kernel through the C ABI (for the roofline timing)."""
+    def op_only(self, ds):
+        """Just the fused loss op through the C ABI (forward launch writes the gradients too)."""
         from deltakd_b200 import functional as Fn
         z, zk, zt, y = ds
-        with torch.no_grad():
-            pass
         return Fn.logit_kd_loss(z, zk, zt, y, kd_kind=self.kind, alpha=self.alpha, tau=self.tau)
 
-    def cpu_step(self, hs):
+    def cpu_prepare(self, hs):
+        return tuple(t.float() for t in hs)  # the reference runs fp32 end to end (SURVEY D5)
+
+    def cpu_step(self, cs):
         from oracle import losses as O
-        if not hasattr(self, "_cpu32"):
-            self._cpu32 = {}
-        key = id(hs)
-        if key not in self._cpu32:  # the reference runs fp32 end to end (SURVEY D5): convert once, outside the timing
-            self._cpu32[key] = tuple(t.float() for t in hs)
-        z, zk, zt, y = self._cpu32[key]
+        from deltakd_b200 import synth
+        z, zk, zt, y = cs
         z = z.detach().requires_grad_(True); zk = zk.detach().requires_grad_(True)
-        l = O.distillation_loss(self.kind, (z, zk), y, zt, None, None, {}, self.args, self.alpha, self.tau)
+        l = O.distillation_loss(self.kind, (z, zk), y, zt, None, None, {}, synth.default_args(), self.alpha, self.tau)
         l.backward()
         return l
 
 
-WORKLOADS = {w.name: w for w in (LogitKD,)}
-DEFAULT = LogitKD.name
+class FeatureKD(Workload):
+    """Feature-level losses: student block outputs [B,197,192], teacher [B,198,384], heads on the student."""
+    kind = ""
+    layers = ()
+    tdtype = torch.float32
+    args_kw = {}
+    M_TOK = 196
+
+    def make_args(self):
+        from deltakd_b200 import synth
+        return synth.default_args(distillation_type=self.kind, **self.args_kw)
+
+    def bytes_per_set(self):
+        return len(self.layers) * self.B * (197 * 192 + 198 * 384) * self.tdtype.itemsize
+
+    def algorithmic_bytes(self):  # per layer: read s, read t, write g_s (SURVEY ยง8d: M*768*elt)
+        return len(self.layers) * self.B * self.M_TOK * 768 * self.tdtype.itemsize
+
+    def host_sets(self, n, B=None):
+        from deltakd_b200 import synth
+        B = B or self.B
+        sets = []
+        for i in range(n):
+            s, t = synth.make_features(B, 1234 + self.rank + 17 * i, layers=self.layers, **getattr(self, "feat_kw", {}))
+            z, _, _, y = synth.make_logits(B, 1000, 99 + self.rank + i)
+            sets.append(dict(s=[None if x is None else _pin(x.to(self.tdtype)) for x in s],
+                             t=[None if x is None else _pin(x.to(self.tdtype)) for x in t],
+                             z=_pin(z), y=_pin(y), noise=_pin(synth.make_noise(B, seed=5 + i))))
+        return sets
+
+    def setup(self):
+        from deltakd_b200 import DistillationLoss, call_base_loss, synth, heads as H
+        self.args = self.make_args()
+        self.teacher = synth.FeatureReplayModel(384)
+        self.student = synth.FeatureReplayModel(192)
+        torch.manual_seed(0)
+        H.attach_distillation_heads(self.student, self.teacher, self.args, "deit_tiny_patch16_224")
+        self.student = self.student.to(self.device)
+        self.crit = DistillationLoss(call_base_loss(self.args), self.teacher, self.kind, 0.1, 3.0)
+        self.inputs = torch.zeros(self.B, 3, 2, 2, device=self.device)
+
+    def to_device(self, hs):
+        mv = lambda x: None if x is None else x.to(self.device, non_blocking=True)
+        d = dict(s=[mv(x) for x in hs["s"]], t=[mv(x) for x in hs["t"]], z=mv(hs["z"]), y=mv(hs["y"]), noise=mv(hs["noise"]))
+        for x in d["s"]:
+            if x is not None:
+                x.requires_grad_(True)
+        d["z"].requires_grad_(True)
+        return d
+
+    def h2d_bytes(self):
+        return self.bytes_per_set() + 2 * self.B * 1000 * 4 + self.B * 196 * 4
+
+    def step(self, ds):
+        from unittest import mock
+        self.teacher.set_outputs(None, ds["t"])
+        for x in ds["s"]:
+            if x is not None:
+                x.grad = None
+        ds["z"].grad = None
+        for p in self.student.parameters():
+            p.grad = None
+        noise = ds["noise"]
+        with mock.patch("torch.rand", side_effect=lambda *a, **k: noise):  # fixed mask noise (graph-capturable)
+            loss = self.crit(self.inputs, ds["z"], self.student, ds["s"], ds["y"], self.args)
+        loss.backward()
+        return loss
+
+    def op_only(self, ds):
+        from unittest import mock
+        from deltakd_b200 import loss as L
+        noise = ds["noise"]
+        with mock.patch("torch.rand", side_effect=lambda *a, **k: noise):
+            return self.feature_loss(L, ds)
+
+    def cpu_prepare(self, hs):
+        return dict(s=[None if x is None else x.float() for x in hs["s"]], t=[None if x is None else x.float() for x in hs["t"]],
+                    z=hs["z"].float(), y=hs["y"].float(), noise=hs["noise"])
+
+    def cpu_step(self, cs):
+        from oracle import losses as O
+        from deltakd_b200 import heads as H
+        if not hasattr(self, "_cpu_heads"):
+            from deltakd_b200 import synth
+            st = synth.FeatureReplayModel(192)
+            torch.manual_seed(0)
+            H.attach_distillation_heads(st, synth.FeatureReplayModel(384), self.make_args(), "deit_tiny_patch16_224")
+            self._cpu_student = st
+        heads = H.head_tensors(self._cpu_student)
+        for p in heads.values():
+            p.grad = None
+        s = [None if x is None else x.detach().requires_grad_(True) for x in cs["s"]]
+        z = cs["z"].detach().requires_grad_(True)
+        l = O.distillation_loss(self.kind, z, cs["y"], None, s, cs["t"], heads, self.make_args(), 0.1, 3.0, noise=cs["noise"])
+        l.backward()
+        return l
 
 
+class CurKDEarly(FeatureKD):
+    """configs[2]: selective layer-wise hidden-state matching, CurKD early phase (layers 0-2), B=512, fp32."""
+    name = "curkd_early_3layers_b512_f32"
+    kind, layers, B, cpu_B = "curkd", (0, 1, 2), 512, 64
+    args_kw = dict(current_epoch=0)
+    dominant = "dkd_align_mse_fwdbwd (planes + 3 tcgen05 GEMMs per layer)"
+
+    def algorithmic_flops(self):
+        return len(self.layers) * 3 * 2.0 * self.B * 196 * 192 * 384
+
+    def feature_loss(self, L, ds):
+        return L.curkd_loss(self.student, ds["s"], ds["t"], self.args)
+
+
+class CurKDMid(CurKDEarly):
+    name = "curkd_mid_4layers_b512_f32"
+    layers = (3, 4, 5, 6)
+    args_kw = dict(current_epoch=120)
+
+
+class MGD(FeatureKD):
+    """configs[3]: MGD masked feature reconstruction with the 2-conv generator, B=512, fp32 in / bf16x3 tensor passes."""
+    name = "mgd_b512_f32"
+    kind, layers, B, cpu_B = "mgd", (11,), 512, 16
+    bound = "tensor"
+    default_steps = 10
+    dominant = "dkd_masked_generation_fwdbwd (implicit-GEMM conv fwd/dgrad/wgrad on tcgen05)"
+
+    def algorithmic_flops(self):  # 6 conv GEMMs + 3 align GEMMs (SURVEY ยง8d cfg4: 1 642 GFLOP at B=512)
+        M = self.B * 196
+        return 6 * 2.0 * M * 3456 * 384 + 3 * 2.0 * M * 192 * 384
+
+    def feature_loss(self, L, ds):
+        return L.mgd_loss(self.student, ds["s"], ds["t"], self.args)
+
+
+class WassL1(FeatureKD):
+    """configs[4] (l1 variant): WassKD sorted-L1 over tokens, layers 0-2, B=512 per GPU (global 1024 at 2 GPUs)."""
+    name = "wasskd_l1_b512_f32"
+    kind, layers, B, cpu_B = "wasskd", (0, 1, 2), 512, 32
+    args_kw = dict(wasskd_type="l1")
+    dominant = "dkd_wass_l1_fwdbwd (align GEMM + on-chip bitonic sort + dgrad/wgrad GEMMs)"
+
+    def algorithmic_flops(self):
+        return len(self.layers) * 3 * 2.0 * self.B * 196 * 192 * 384
+
+    def feature_loss(self, L, ds):
+        from deltakd_b200 import functional as Fn
+        return Fn.wass_l1_loss(ds["s"][:3], ds["t"][:3], list(self.student.align_wasskd), weight=5.0)
+
+
+HEADLINE = LogitKD
+EXTRAS = (CurKDEarly, CurKDMid, MGD, WassL1)
+WORKLOADS = {w.name: w for w in (HEADLINE,) + EXTRAS}
+
+
+# ----------------------------------------------------------------------------- measurement
 def cpu_baseline(w: Workload, budget_s: float = 12.0, max_steps: int = 20000):
     torch.set_num_threads(os.cpu_count() or 1)
-    hs = w.host_sets(2)
-    w.cpu_step(hs[0])
+    Bc = w.cpu_B or w.B
+    cs = [w.cpu_prepare(h) for h in w.host_sets(2, B=Bc)]
+    w.cpu_step(cs[0])
     t0 = time.perf_counter(); n = 0
     while True:
-        w.cpu_step(hs[n % 2]); n += 1
+        w.cpu_step(cs[n % 2]); n += 1
         dt = time.perf_counter() - t0
         if dt > budget_s or n >= max_steps:
             break
-    return {"value": w.B * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} steps of {w.name} (fp32 torch-CPU oracle of the reference loss, fwd+bwd), {dt:.1f} s"}, dt / n
+    return {"value": Bc * n / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of {w.name} at batch {Bc} (fp32 torch-CPU oracle of the reference loss, fwd+bwd), {dt:.1f} s"}
 
 
 def run_reference(args, w_cls):
     """Reference arm: the reference's CPU implementation of the path (oracle port), all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     w = w_cls(torch.device("cpu"), 0)
-    from deltakd_b200.synth import default_args
-    w.args = default_args()
     torch.set_num_threads(os.cpu_count() or 1)
-    hs = w.host_sets(2)
+    Bc = w.cpu_B or w.B
+    cs = [w.cpu_prepare(h) for h in w.host_sets(2, B=Bc)]
     for i in range(max(args.warmup, 1)):
-        w.cpu_step(hs[i % 2])
-    # each step = one batch; bounded so K steps end within minutes
+        w.cpu_step(cs[i % 2])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        w.cpu_step(hs[i % 2])
+        w.cpu_step(cs[i % 2])
     dt = time.perf_counter() - t0
-    v = w.B * args.steps / dt
+    v = Bc * args.steps / dt
+    sample = f"{args.steps} steps of {w.name} at batch {Bc}"
     print(json.dumps({
-        "impl": "reference", "metric": "distill-loss fwd+bwd samples/s", "value": v, "unit": "samples/s",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "note": "reference loss path restated for CPU (oracle port), torch CPU fp32"},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} steps of {w.name}"},
+        "config": {"workload": w.name, "note": "reference loss path restated for CPU (oracle port), torch CPU fp32, "
+                   "all host threads; the reference is pure PyTorch and is not present on the GPU box"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def _graph_of(fn, reps):
+    """Capture `reps` calls of fn() into one CUDA graph (after a side-stream warm-up call)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn(0)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        last = None
+        for i in range(reps):
+            last = fn(i)
+    g.replay()  # untimed: graph upload
+    torch.cuda.synchronize()
+    return g, last
+
+
+def _timed_replay(g, barrier):
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1), (t0, time.time())
+
+
+def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_cpu: bool):
+    from deltakd_b200 import _lib
+    w.setup()
+    nsets = w.nsets()
+    host = w.host_sets(nsets)
+    dsets = [w.to_device(h) for h in host]
+    torch.cuda.synchronize()
+    windows = []
+
+    # ---- device-resident throughput: eager warm-up, then K steps replayed from a CUDA graph
+    for i in range(W):
+        w.step(dsets[i % nsets])
+    torch.cuda.synchronize()
+    c0 = _lib.lib.dkd_launch_count()
+    graph, last = _graph_of(lambda i: w.step(dsets[(W + i) % nsets]), K)
+    launches = (_lib.lib.dkd_launch_count() - c0) * K // (K + 1)   # the capture pass ran fn K+1 times
+    ms, win = _timed_replay(graph, barrier)
+    windows.append(win)
+    loss_val = float(last.item())
+    del graph
+
+    # ---- the fused loss op alone (C-ABI call without the autograd rescale), same rotation, own graph
+    with torch.no_grad():
+        pass
+    kg, _ = _graph_of(lambda i: w.op_only(dsets[(W + i) % nsets]), K)
+    k_ms, win = _timed_replay(kg, barrier)
+    windows.append(win)
+    k_ms /= K
+    del kg
+
+    # ---- end to end through the public API with host buffers
+    for i in range(W):
+        w.step(w.to_device(host[i % nsets])).item()
+    barrier()
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e2.record()
+    for i in range(K):
+        w.step(w.to_device(host[(W + i) % nsets])).item()
+    e3.record()
+    torch.cuda.synchronize()
+    windows.append((t0, time.time()))
+    ms_e2e = e2.elapsed_time(e3)
+    ms, ms_e2e = allmax([ms, ms_e2e])
+
+    if w.bound == "hbm":
+        ach, peak, unit, alg = w.algorithmic_bytes() / (k_ms * 1e-3) / 1e9, pk["hbm"], "GB/s", w.algorithmic_bytes()
+    else:
+        ach, peak, unit, alg = w.algorithmic_flops() / (k_ms * 1e-3) / 1e12, pk["bf16_sus"], "TFLOP/s", w.algorithmic_flops()
+    res = {
+        "workload": w.name, "value": world * w.B * K / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / K, "steps": K,
+        "dtype": w.dtype, "batch_per_gpu": w.B, "loss": loss_val,
+        "l2": (f"{nsets} rotating input sets ({nsets * w.bytes_per_set() / 2**20:.0f} MiB > 126 MiB L2)" if nsets > 1
+               else f"one input set of {w.bytes_per_set() / 2**20:.0f} MiB (> 126 MiB L2)"),
+        "e2e": {"value": world * w.B * K / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": w.h2d_bytes(),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": w.bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+                     "kernel": w.dominant, "kernel_us": k_ms * 1e3, "peak_source": pk["src"],
+                     ("algorithmic_bytes" if w.bound == "hbm" else "algorithmic_flops"): alg},
+    }
+    if w.bound == "hbm" and w.algorithmic_flops():
+        res["roofline"]["algorithmic_flops"] = w.algorithmic_flops()
+    if with_cpu:
+        res["cpu_baseline"] = cpu_baseline(w, budget_s=12.0 if isinstance(w, LogitKD) else 6.0)
+    del dsets, host
+    torch.cuda.empty_cache()
+    return res, windows
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=DEFAULT, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=HEADLINE.name, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline workload only")
     args = ap.parse_args()
     w_cls = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = w_cls.default_steps
     if args.impl == "reference":
         return run_reference(args, w_cls)
 
@@ -243,107 +507,47 @@ def main():
     if dist_on:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    W = max(args.warmup, 3)
-    K = args.steps
-    pk = peaks()
 
-    w = w_cls(dev, rank)
-    w.setup()
-    nsets = w.nsets()
-    host = w.host_sets(nsets)
-    dsets = [w.to_device(h) for h in host]
-    torch.cuda.synchronize()
-
-    sampler = ClockSampler(local).start() if rank == 0 else None
-
-    # ---- device-resident throughput: warm up eagerly, then capture K steps into a CUDA graph --------
-    for i in range(W):
-        w.step(dsets[i % nsets])
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        w.step(dsets[0])
-    torch.cuda.current_stream().wait_stream(side)
-    with torch.cuda.graph(graph):
-        for i in range(K):
-            last = w.step(dsets[(W + i) % nsets])
-    graph.replay()  # one untimed replay (graph upload)
-    torch.cuda.synchronize()
-    if dist_on:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    e0.record()
-    graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    if dist_on:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    loss_val = float(last.item())
-
-    # ---- dominant kernel alone: events around each launch ------------------------------------------
-    evs = []
-    for i in range(min(K, 200)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ds = dsets[(i * 7) % nsets]
-        a.record(); w.kernel_only(ds); b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    kms = sorted(a.elapsed_time(b) for a, b in evs)
-    k_ms = sum(kms) / len(kms)
-
-    # ---- end to end through the public API with host buffers ---------------------------------------
-    for i in range(W):
-        l = w.step(w.to_device(host[i % nsets])); l.item()
-    torch.cuda.synchronize()
-    if dist_on:
-        dist.barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for i in range(K):
-        l = w.step(w.to_device(host[(W + i) % nsets]))
-        l.item()
-    e3.record()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    ms_e2e = e2.elapsed_time(e3)
-
-    if dist_on:
-        t = torch.tensor([ms, ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
-    if rank != 0:
+    def barrier():
         if dist_on:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
 
-    clocks = sampler.stop(t_wall0, t_wall1)
-    n = world
-    value = n * w.B * K / (ms * 1e-3)
-    e2e_v = n * w.B * K / (ms_e2e * 1e-3)
-    ach = w.algorithmic_bytes() / (k_ms * 1e-3) / 1e9
-    out = {
-        "metric": "distill-loss fwd+bwd samples/s", "value": value, "unit": "samples/s", "n_gpus": n, "steps": K,
-        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": w.dtype, "data": "synthetic",
-        "config": {"workload": w.name, "batch_per_gpu": w.B, "timing": "CUDA-graph replay of K steps, CUDA events",
-                   "l2": f"{nsets} rotating input sets ({nsets * w.bytes_per_set() / 2**20:.0f} MiB > 126 MiB L2)",
-                   "teacher": "teacher outputs replayed (inputs of the loss path)", "loss": loss_val},
-        "e2e": {"value": e2e_v, "unit": "samples/s", "h2d_bytes_per_step": w.h2d_bytes(), "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": K * w.launches_per_step,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                     "traffic": None, "kernel": w.dominant, "kernel_us": k_ms * 1e3, "peak_source": pk["src"],
-                     "algorithmic_bytes": w.algorithmic_bytes()},
-        "clocks": clocks,
-    }
-    if not args.no_cpu_baseline:
-        out["cpu_baseline"], _ = cpu_baseline(w)
-    print(json.dumps(out))
+    def allmax(vals):
+        if not dist_on:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    W = max(args.warmup, 3)
+    pk = peaks()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+
+    head, windows = measure(w_cls(dev, rank), args.steps, W, world, barrier, allmax, pk, with_cpu)
+    extras = []
+    if not args.no_extras and w_cls is HEADLINE:
+        for cls in EXTRAS:
+            r, win = measure(cls(dev, rank), min(args.steps, cls.default_steps), W, world, barrier, allmax, pk, with_cpu)
+            extras.append(r)
+            windows += win
+
+    if rank == 0:
+        clocks = sampler.stop(windows)
+        out = {
+            "metric": METRIC, "value": head["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
+            "config": {"workload": head["workload"], "batch_per_gpu": head["batch_per_gpu"],
+                       "timing": "CUDA-graph replay of K steps, CUDA events, max over ranks", "l2": head["l2"],
+                       "teacher": "teacher outputs replayed (inputs of the loss path)", "loss": head["loss"]},
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": clocks,
+        }
+        if "cpu_baseline" in head:
+            out["cpu_baseline"] = head["cpu_baseline"]
+        if extras:
+            out["workloads"] = extras
+        print(json.dumps(out))
     if dist_on:
         dist.destroy_process_group()
 

@@ -30,6 +30,7 @@ SIGNATURES = {
     "dkd_version": (_i, []),
     "dkd_last_error": (C.c_char_p, []),
     "dkd_check_device": (_i, []),
+    "dkd_launch_count": (C.c_ulonglong, []),
     "dkd_logit_kd_workspace_bytes": (_sz, [_i64]),
     "dkd_logit_kd_fwdbwd": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _i, _f, _f, _f, _p, _p, _p, _p, _sz, _p]),
     "dkd_mask_rank": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
@@ -37,6 +38,11 @@ SIGNATURES = {
     "dkd_align_mse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_masked_generation_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_masked_generation_fwdbwd": (_i, [_p] * 10 + [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _f] + [_p] * 10 + [_sz, _p]),
+    "dkd_wass_l1_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
+    "dkd_wass_l1_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "dkd_saliency_selfdiag_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "dkd_saliency_selfdiag_score": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _sz, _p]),
+    "dkd_saliency_cls_score": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p]),
     "dkd_align_mse_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
 }
 

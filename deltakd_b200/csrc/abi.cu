@@ -5,6 +5,7 @@
 
 namespace dkd {
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels enqueued by this library (all threads; statistics only)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -14,6 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -28,6 +30,8 @@ extern "C" {
 int dkd_version(void) { return 100; }
 
 const char* dkd_last_error(void) { return dkd::g_err; }
+
+unsigned long long dkd_launch_count(void) { return __atomic_load_n(&dkd::g_launches, __ATOMIC_RELAXED); }
 
 int dkd_check_device(void) {
   int dev = 0, major = 0;

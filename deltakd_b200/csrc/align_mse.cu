@@ -119,7 +119,7 @@ int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const flo
     if (rc != DKD_OK) return rc;
     p.ld.k_blocks = Dt / 64;
     p.ld.nterms = P == 2 ? 3 : 1;
-    p.ep.out = g_s; p.ep.drop_mask = nullptr; p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off;
+    p.ep.out = g_s; p.ep.drop_mask = nullptr; p.ep.bias = nullptr; p.ep.alpha = 1.f; p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off;
     p.ep.out_is_bf16 = dtype == DKD_BF16;
     p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM);
     p.n_tiles = Ds / Cfg::BN;

@@ -40,7 +40,8 @@ struct ConvRowsLoader {
     const int term = kit / KB, r = kit - term * KB;
     const int tap = r / 6, cb = r - tap * 6;
     const int dy = tap / 3, dx = tap - dy * 3;
-    const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+    int pa, pb;
+    term_planes(term, p.nterms, pa, pb);
 #pragma unroll
     for (int rr = 0; rr < ROWS; ++rr) {
       const int hb = mt * ROWS + rr;
@@ -159,8 +160,9 @@ struct NtConvLoader {
     it.dcol_off = -1;
     it.aux = tap;
   }
-  static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
-    const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+  static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int nterms, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    int pa, pb;
+    term_planes(term, nterms, pa, pb);
     const int dy = it.aux / 3, dx = it.aux - dy * 3;
     sm100::tma_load_3d(a, &p.tmG, bar, it.a_col0, rb * Cfg::KROWS, pa);
     sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmG, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);

@@ -43,7 +43,7 @@ __device__ __forceinline__ void epilogue_block_partial(float acc, int tid, doubl
 int launch_fold_partials(const double* partials, int n, float scale, float* loss, cudaStream_t st);
 
 struct ResidualMseParams {
-  const void* t;          // teacher [B, Tt, N] (fp32 or bf16), rows b*Tt + t_off + i
+  const void* t;          // teacher [B, Tt, N] (fp32 or bf16), rows b*Tt + t_off + i; null -> no subtraction
   const float* bias;      // [N] or null
   __nv_bfloat16* G;       // planes [P][M][N]
   double* partials;       // [gridDim.x]
@@ -69,7 +69,10 @@ struct ResidualMseEpi {
       float v[32];
       sm100::tmem_ld32(t_acc + c0, v);
       float tv[32];
-      if (live) {
+      if (p.t == nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tv[j] = 0.f;
+      } else if (live) {
         if (p.t_is_bf16) {
           const __nv_bfloat16* tp = reinterpret_cast<const __nv_bfloat16*>(p.t) + trow * p.N + n0 + c0;
 #pragma unroll
@@ -116,6 +119,8 @@ struct ResidualMseEpi {
 struct StoreRowsParams {
   void* out;              // [B, T_out, N_total] fp32 or bf16; rows b*T_out + off + i
   const float* drop_mask; // [M] 0/1 or null: rows with mask != 0 are stored as zeros
+  const float* bias;      // [N_total] added after scaling, or null
+  float alpha;            // out = alpha * acc (+ bias)
   int64_t M;
   int N_total, n_tok, T_out, off;
   int out_is_bf16;
@@ -141,6 +146,9 @@ struct StoreRowsEpi {
       if (p.drop_mask != nullptr && __ldg(p.drop_mask + m) != 0.f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
       }
       float z[32];
 #pragma unroll

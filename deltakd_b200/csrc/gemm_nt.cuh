@@ -40,10 +40,12 @@ struct GemmNtCfg {
 };
 
 struct NtEpilogueParams {
-  float* D;      // fp32, += via red.add
-  float* Dcol;   // += column NB_DATA of the tile (ones trick), or null
-  int ldd;
-  float alpha;
+  float* D = nullptr;     // fp32, += via red.add (or plain stores when `store`)
+  float* Dcol = nullptr;  // += column NB_DATA of the tile (ones trick), or null
+  int ldd = 0;
+  float alpha = 1.f;
+  int store = 0;          // 1: the tile is written with plain stores (each item owns its output, e.g. per-split partials)
+  int rows_valid = 128;   // output rows of the 128-row tile that exist (A narrower than 128 columns)
 };
 
 // Loader policy interface:
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           for (int rb = it.rb0; rb < it.rb1; ++rb) {
             mbar_wait(&empty[s], ph ^ 1);
             mbar_expect_tx(&full[s], Loader::TX_BYTES);
-            Loader::issue(p.ld, it, term, rb, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
+            Loader::issue(p.ld, it, term, p.nterms, rb, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -145,19 +147,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16);
       float* drow = p.ep.D + it.d_off + (size_t)row * p.ep.ldd;
+      const bool row_ok = row < p.ep.rows_valid;
 #pragma unroll 1
       for (int c0 = 0; c0 < Cfg::NB_DATA; c0 += 32) {
         float v[32];
         tmem_ld32(t_acc + c0, v);
         tmem_ld_wait();
+        if (!row_ok) continue;
+        if (p.ep.store) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j] * p.ep.alpha);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(drow + c0 + j) =
+                make_float4(v[j] * p.ep.alpha, v[j + 1] * p.ep.alpha, v[j + 2] * p.ep.alpha, v[j + 3] * p.ep.alpha);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j] * p.ep.alpha);
+        }
       }
       if constexpr (Cfg::ONES) {
         float v[32];
         tmem_ld32(t_acc + Cfg::NB_DATA - 16, v);  // columns NB_DATA-16 .. NB_DATA+15 (inside the allocation)
         tmem_ld_wait();
-        if (p.ep.Dcol && it.dcol_off >= 0) atomicAdd(p.ep.Dcol + it.dcol_off + row, v[16] * p.ep.alpha);
+        if (row_ok && p.ep.Dcol && it.dcol_off >= 0) atomicAdd(p.ep.Dcol + it.dcol_off + row, v[16] * p.ep.alpha);
       }
       tc_fence_before();
       __syncwarp();
@@ -208,8 +219,9 @@ struct NtPlainLoader {
     it.dcol_off = tile * 128;
     it.aux = 0;
   }
-  static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
-    const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+  static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int nterms, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    int pa, pb;
+    term_planes(term, nterms, pa, pb);
     sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
     sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
 #pragma unroll

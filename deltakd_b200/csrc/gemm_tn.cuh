@@ -170,7 +170,8 @@ struct PlaneLoader {
   }
   static __device__ __forceinline__ void issue(const Params& p, int kit, int mt, int nt, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
     const int term = kit / p.k_blocks, kb = kit - term * p.k_blocks;
-    const int pa = term == 2 ? 1 : 0, pb = term == 1 ? 1 : 0;
+    int pa, pb;
+    term_planes(term, p.nterms, pa, pb);
     sm100::tma_load_3d(sA, &p.tmA, bar, kb * 64, mt * Cfg::BM, pa);
 #pragma unroll
     for (int i = 0; i < Cfg::BN / B_BOX_ROWS; ++i)

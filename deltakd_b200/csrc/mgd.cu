@@ -241,7 +241,7 @@ int dkd_masked_generation_fwdbwd(const void* s, const void* t, const float* mask
     rc = make_plane_tmap(&p.ld.tmB, ws.Wat, P, Ds, Dt, Dt, (int64_t)Dt * Ds, Cfg::BN, "mgd W_align^T");
     if (rc != DKD_OK) return rc;
     p.ld.k_blocks = Dt / 64; p.ld.nterms = nterms;
-    p.ep.out = g_s; p.ep.drop_mask = mask; p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off;
+    p.ep.out = g_s; p.ep.drop_mask = mask; p.ep.bias = nullptr; p.ep.alpha = 1.f; p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off;
     p.ep.out_is_bf16 = dtype == DKD_BF16;
     p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM); p.n_tiles = Ds / Cfg::BN;
     rc = launch_tn<Cfg, L, E>(p, st, "mgd: align dgrad");

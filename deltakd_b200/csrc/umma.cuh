@@ -160,6 +160,25 @@ __device__ __forceinline__ uint64_t mnmajor_desc(uint32_t smem_addr, uint32_t mn
 
 }  // namespace sm100
 
+// Split-bf16 term schedules.  A value is carried as 1, 2 or 3 bf16 planes (hi, mid, lo: 8 + 8 + 8 mantissa bits).
+//   nterms 1 : hi*hi                                            (plain bf16)
+//   nterms 3 : hi*mid + mid*hi + hi*hi                          ("bf16x3", ~2^-16 relative)
+//   nterms 6 : hi*lo + lo*hi + mid*mid + hi*mid + mid*hi + hi*hi ("bf16x6", ~2^-24: fp32-exact operands)
+// The small cross terms are accumulated FIRST and hi*hi last: the tensor core's fp32 accumulation rounds
+// relative to the running magnitude, so keeping the accumulator small for most of the chain cuts the
+// accumulated rounding bias.
+__device__ __forceinline__ void term_planes(int term, int nterms, int& pa, int& pb) {
+  if (nterms == 1) { pa = 0; pb = 0; return; }
+  if (nterms == 3) {
+    pa = term == 1 ? 1 : 0;
+    pb = term == 0 ? 1 : 0;
+    return;
+  }
+  // nterms == 6 : (0,2) (2,0) (1,1) (0,1) (1,0) (0,0)
+  pa = term == 1 ? 2 : (term == 2 || term == 4) ? 1 : 0;
+  pb = term == 0 ? 2 : (term == 2 || term == 3) ? 1 : 0;
+}
+
 // ---- host: tensor maps (driver entry point resolved at run time; no link-time libcuda) --------
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const char* what);

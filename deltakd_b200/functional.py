@@ -178,7 +178,7 @@ class _AlignMseLayers(torch.autograd.Function):
     """sum_i scale * || Linear_i(s_i[:, 1:]) - t_i[:, 2:] ||^2 over the selected layers (fused fwd+bwd)."""
 
     @staticmethod
-    def forward(ctx, scale, n_layers, s_off, t_off, *tensors):
+    def forward(ctx, entry, scale, n_layers, s_off, t_off, *tensors):
         s_list = tensors[:n_layers]
         t_list = tensors[n_layers:2 * n_layers]
         w_list = tensors[2 * n_layers:3 * n_layers]
@@ -193,15 +193,15 @@ class _AlignMseLayers(torch.autograd.Function):
             n_tok = Ts - s_off
             dt = _dtype_code(s)
             prec = _precision_for(s)
-            need_s = ctx.needs_input_grad[4 + i]
-            need_w = ctx.needs_input_grad[4 + 2 * n_layers + i]
-            need_b = b is not None and ctx.needs_input_grad[4 + 3 * n_layers + i]
+            need_s = ctx.needs_input_grad[5 + i]
+            need_w = ctx.needs_input_grad[5 + 2 * n_layers + i]
+            need_b = b is not None and ctx.needs_input_grad[5 + 3 * n_layers + i]
             g_s = torch.empty_like(s) if need_s else None
             g_W = torch.empty_like(W) if (need_w or need_b) else None
             g_b = torch.empty_like(b) if need_b else None
-            nbytes = _lib.lib.dkd_align_mse_workspace_bytes(B, n_tok, Ds, Dt, prec)
-            ws = _scratch(dev, "align_mse", nbytes)
-            _lib.call("dkd_align_mse_fwdbwd", _ptr(s), _ptr(t), _ptr(W), _ptr(b), B, Ts, s_off, Tt, t_off, n_tok,
+            nbytes = getattr(_lib.lib, entry + "_workspace_bytes")(B, n_tok, Ds, Dt, prec)
+            ws = _scratch(dev, entry, nbytes)
+            _lib.call(entry + "_fwdbwd", _ptr(s), _ptr(t), _ptr(W), _ptr(b), B, Ts, s_off, Tt, t_off, n_tok,
                       Ds, Dt, dt, prec, float(scale), _ptr(g_s), _ptr(g_W), _ptr(g_b), _ptr(loss), _ptr(ws),
                       ws.numel(), _stream())
             grads.append((g_s, g_W if need_w else None, g_b))
@@ -219,7 +219,7 @@ class _AlignMseLayers(torch.autograd.Function):
         gs = [g[0] for g in grads]
         gw = [g[1] for g in grads]
         gb = [g[2] for g in grads]
-        return (None, None, None, None, *gs, *([None] * n), *gw, *gb)
+        return (None, None, None, None, None, *gs, *([None] * n), *gw, *gb)
 
 
 def _check_feature_pair(s, t, s_off, t_off):
@@ -230,7 +230,8 @@ def _check_feature_pair(s, t, s_off, t_off):
         raise ValueError(f"patch-token counts differ: student {s.shape[1] - s_off} vs teacher {t.shape[1] - t_off}")
 
 
-def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 1, t_off: int = 2):
+def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 1, t_off: int = 2,
+                          _entry: str = "dkd_align_mse"):
     """scale * sum_i sum((linears[i](s_feats[i][:, s_off:]) - t_feats[i][:, t_off:])**2), 0-dim fp32."""
     n = len(linears)
     s_list, t_list, w_list, b_list = [], [], [], []
@@ -243,7 +244,17 @@ def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 
         t_list.append(t.contiguous())
         w_list.append(lin.weight.float().contiguous() if lin.weight.dtype != torch.float32 else lin.weight.contiguous())
         b_list.append(None if lin.bias is None else lin.bias.float().contiguous())
-    return _AlignMseLayers.apply(scale, n, s_off, t_off, *s_list, *t_list, *w_list, *b_list)
+    return _AlignMseLayers.apply(_entry, scale, n, s_off, t_off, *s_list, *t_list, *w_list, *b_list)
+
+
+def wass_l1_loss(s_feats, t_feats, linears, weight: float = 5.0, s_off: int = 1, t_off: int = 2):
+    """weight * mean_i mean|sort_tokens(linears[i](s_i[:, s_off:])) - sort_tokens(t_i[:, t_off:])| (loss.py:187-199,226).
+    `weight` (the reference's x5) is folded into the kernels so backward needs no rescale pass."""
+    n = len(linears)
+    B, Ts, _ = s_feats[0].shape
+    Dt = t_feats[0].shape[-1]
+    numel = B * (Ts - s_off) * Dt
+    return align_mse_layers_loss(s_feats, t_feats, linears, weight / (n * numel), s_off, t_off, _entry="dkd_wass_l1")
 
 
 # --------------------------------------------------------------------------- masked generation (MGD family)
@@ -316,3 +327,71 @@ def mask_rank(score: torch.Tensor, len_keep: int, want_shuffle: bool = True):
     _lib.call("dkd_mask_rank", _ptr(score), B, L, int(len_keep), _ptr(mask), _ptr(ids_restore),
               _ptr(ids_shuffle), _stream())
     return mask, ids_restore, ids_shuffle
+
+
+# --------------------------------------------------------------------------- saliency scores (no gradient)
+def _token_rows(x: torch.Tensor):
+    """(tensor, T) such that token i of sample b starts at data_ptr + (b*T + i)*D elements; copies only if the
+    view is not row-contiguous (a `feat[:, 2:]` slice of a contiguous [B, T, D] tensor is used in place)."""
+    B, n, D = x.shape
+    if x.stride(2) == 1 and x.stride(1) == D and (B == 1 or (x.stride(0) % D == 0 and x.stride(0) >= n * D)):
+        return x, (n if B == 1 else x.stride(0) // D)
+    x = x.contiguous()
+    return x, n
+
+
+def saliency_score_selfdiag(x, qk_weight, qk_bias, num_heads: int = 8):
+    """SimpleAttention.forward (models.py:46-56): [B, N, D] tokens -> [B, N] head-mean diagonal of softmax(QK^T/sqrt(hd))."""
+    _require_cuda(x, qk_weight)
+    x = x.detach()
+    x, T = _token_rows(x)
+    B, n, D = x.shape
+    prec = _precision_for(x)
+    score = torch.empty(B, n, dtype=torch.float32, device=x.device)
+    nbytes = _lib.lib.dkd_saliency_selfdiag_workspace_bytes(B, n, D, prec)
+    ws = _scratch(x.device, "saliency", nbytes)
+    f32 = lambda w: None if w is None else w.detach().float().contiguous()
+    w, b = f32(qk_weight), f32(qk_bias)
+    _lib.call("dkd_saliency_selfdiag_score", _ptr(x), B, T, 0, n, D, _dtype_code(x), _ptr(w), _ptr(b), num_heads, prec,
+              _ptr(score), _ptr(ws), ws.numel(), _stream())
+    return score
+
+
+def _cls_score(xq, xq_stride, xk, xk_stride, n_keys, B, D, dt, wq, bq, wk, bk, num_heads, query_is_key, device):
+    score = torch.empty(B, n_keys, dtype=torch.float32, device=device)
+    _lib.call("dkd_saliency_cls_score", xq, xq_stride, xk, xk_stride, n_keys, B, D, dt, _ptr(wq), _ptr(bq), _ptr(wk),
+              _ptr(bk), num_heads, query_is_key, _ptr(score), _stream())
+    return score
+
+
+def saliency_score_cls_row(teacher_feat, qk_weight, qk_bias, num_heads: int = 8):
+    """saliency_masking method 2 (misc.py:88-116): teacher_feat [B, 2+N, D] with CLS, DIST at 0, 1; CLS-query attention
+    over [CLS] + patches, head-mean, patch columns only -> [B, N]."""
+    _require_cuda(teacher_feat, qk_weight)
+    t = teacher_feat.detach().contiguous()
+    B, Tt, D = t.shape
+    w = qk_weight.detach().float().contiguous()
+    b = None if qk_bias is None else qk_bias.detach().float().contiguous()
+    esz = t.element_size()
+    xk = C.c_void_p(t.data_ptr() + 2 * D * esz)
+    wk = w[D:]
+    bk = None if b is None else b[D:]
+    return _cls_score(_ptr(t), Tt * D, xk, Tt * D, Tt - 2, B, D, _dtype_code(t), w, b, wk, bk, num_heads, 1, t.device)
+
+
+def saliency_score_cross(x_query, x_key, q_weight, q_bias, k_weight, k_bias, num_heads: int = 8):
+    """SimpleCrossAttention.forward (models.py:24-35) for one query token per sample: -> [B, 1, Nk]."""
+    _require_cuda(x_query, x_key, q_weight, k_weight)
+    if x_query.dim() != 3 or x_query.shape[1] != 1:
+        raise ValueError("saliency_score_cross supports a single query token per sample ([B, 1, D])")
+    xq = x_query.detach()
+    xk, Tk = _token_rows(x_key.detach())
+    if xq.dtype != xk.dtype:
+        xq = xq.to(xk.dtype)
+    if xq.stride(2) != 1:
+        xq = xq.contiguous()
+    B, n, D = xk.shape
+    f32 = lambda w: None if w is None else w.detach().float().contiguous()
+    s = _cls_score(_ptr(xq), xq.stride(0) if B > 1 else D, _ptr(xk), Tk * D, n, B, D, _dtype_code(xk), f32(q_weight), f32(q_bias),
+                   f32(k_weight), f32(k_bias), num_heads, 0, xk.device)
+    return s.unsqueeze(1)

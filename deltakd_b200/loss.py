@@ -120,13 +120,14 @@ class DistillationLoss(nn.Module):
         if kind == 'saliency_mgd':
             return base_loss + saliency_mgd_loss(student, student_features, teacher_features, args)
         if kind == 'wasskd':
+            # the reference's `loss_wass / 3 * 5.0` (loss.py:199,225-226) is folded into the kernels
             if args.wasskd_type == 'l1':
-                w = Fn.wass_l1_loss(student_features[:3], teacher_features[:3], student.align_wasskd)
+                w5 = Fn.wass_l1_loss(student_features[:3], teacher_features[:3], list(student.align_wasskd), weight=5.0)
             elif args.wasskd_type == 'sinkhorn':
-                w = Fn.wass_sinkhorn_loss(student_features[:3], teacher_features[:3], student.align_wasskd)
+                w5 = Fn.wass_sinkhorn_loss(student_features[:3], teacher_features[:3], list(student.align_wasskd), weight=5.0)
             else:
                 return base_loss  # loss.py:186-226: unknown type leaves loss_wass = 0.0
-            return base_loss + w * 5.0
+            return base_loss + w5
         # kind == 'mgd'
         return base_loss + mgd_loss(student, student_features, teacher_features, args)
 
@@ -168,7 +169,7 @@ def saliency_mgd_loss(student_model, student_features, teacher_features, args):
 def curkd_loss(student_model, student_features, teacher_features, args):
     """loss.py:362-420: curriculum over args.current_epoch (<100: layers 0-2, <151: layers 3-6,
     else masked generation on layer 11 with the mask ratio fixed at 0.5)."""
-    B = student_features[0].shape[0]
+    B = next(f for f in student_features if f is not None).shape[0]  # callers may pass only the selected layers
     epoch = args.current_epoch
     if epoch < 100:
         return Fn.align_mse_layers_loss(student_features[0:3], teacher_features[0:3],

@@ -58,6 +58,9 @@ DKD_API int dkd_version(void);
 DKD_API const char* dkd_last_error(void);
 /* DKD_OK when the current CUDA device is compute capability 10.x, else DKD_E_ARCH. */
 DKD_API int dkd_check_device(void);
+/* Number of CUDA kernels this library has enqueued since it was loaded (statistics for bench.py's
+ * `gpu_launches`; under CUDA-graph capture it counts the captured launches once). */
+DKD_API unsigned long long dkd_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Logit losses: base CE + soft / hard KD, forward and backward in one launch.
@@ -124,6 +127,21 @@ DKD_API int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, c
                                  size_t workspace_bytes, dkd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * WassKD 'l1' term of one layer, forward + backward:
+ *     a = s[:, s_off:, :] W^T + bias ;  per (sample, channel): sort the n_tok values of a and of t[:, t_off:, :]
+ *     *loss += scale * sum |sort(a) - sort(t)|                (accumulates)
+ *     g_a[b, pi(r), d] = scale * sign(sorted_a - sorted_t)[b, r, d]  -> g_s, g_W, g_b   (overwritten)
+ * Replaces model/loss.py:187-199 (torch.sort over dim=1 of both tensors, mean |diff|) and its backward;
+ * the caller folds 5/(3*B*n_tok*Dt) into `scale`.  Same argument conventions as dkd_align_mse_fwdbwd;
+ * n_tok <= 256.  Ties in the student sort are ordered by token index.
+ */
+DKD_API size_t dkd_wass_l1_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
+DKD_API int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float* bias, int64_t B, int Ts, int s_off,
+                               int Tt, int t_off, int n_tok, int Ds, int Dt, int dtype, int precision, float scale,
+                               void* g_s, float* g_W, float* g_b, float* loss, void* workspace, size_t workspace_bytes,
+                               dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Masked generative distillation core, forward + backward (14x14 token grid, Ds = 192, Dt = 384):
  *     x   = s[:, s_off:, :] W_align^T + b_align
  *     x_m = where(mask, mask_token, x)
@@ -144,6 +162,27 @@ DKD_API int dkd_masked_generation_fwdbwd(const void* s, const void* t, const flo
                                          float scale, void* g_s, float* g_W_align, float* g_b_align, float* g_mask_token,
                                          float* g_conv1_w, float* g_conv1_b, float* g_conv2_w, float* g_conv2_b,
                                          float* loss, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Saliency scores for saliency-MGD (no gradient).  Replace SimpleAttention / SimpleCrossAttention
+ * (model/models.py:14-56) as used by saliency_masking (model/misc.py:62-70, 88-116, 135-148); the
+ * ascending order of the score picks the kept tokens (dkd_mask_rank).  8 heads x 48 (D = 384).
+ *
+ * dkd_saliency_selfdiag_score — method 1: score[b,i] = mean_h softmax_j(q_i.k_j / sqrt(48))[i] over the n_tok
+ *   patch tokens x[b, off + i, :] of x [B, T, D] (`dtype`); qk_w [2D, D], qk_b [2D] fp32 (q = first D outputs).
+ *   The qk projection runs on tcgen05 (`precision`), the attention maps are never materialised.
+ * dkd_saliency_cls_score — methods 2 and 3: one query token per sample (xq + b*xq_stride, strides in elements)
+ *   against n_keys key tokens (xk + b*xk_stride + j*D); separate q / k projections Wq,bq / Wk,bk ([D,D],[D], fp32;
+ *   biases may be NULL).  query_is_key != 0 also counts the query token as key 0 of the softmax and drops its
+ *   column from the output (method 2: CLS row over [CLS]+patches).  score: fp32 [B, n_keys].
+ */
+DKD_API size_t dkd_saliency_selfdiag_workspace_bytes(int64_t B, int n_tok, int D, int precision);
+DKD_API int dkd_saliency_selfdiag_score(const void* x, int64_t B, int T, int off, int n_tok, int D, int dtype,
+                                        const float* qk_w, const float* qk_b, int num_heads, int precision, float* score,
+                                        void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+DKD_API int dkd_saliency_cls_score(const void* xq, int64_t xq_stride, const void* xk, int64_t xk_stride, int n_keys,
+                                   int64_t B, int D, int dtype, const float* Wq, const float* bq, const float* Wk,
+                                   const float* bk, int num_heads, int query_is_key, float* score, dkd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -182,25 +182,25 @@ def mgd(s_feats, t_feats, heads, mgd_alpha: float, mask_ratio: float, noise, pro
     return masked_generation_sse(x, mask, t, heads, probe) / t.numel() * mgd_alpha
 
 
-def saliency_mgd(s_feats, t_feats, heads, mask_ratio: float, method: int) -> torch.Tensor:
+def saliency_mgd(s_feats, t_feats, heads, mask_ratio: float, method: int, probe=None) -> torch.Tensor:
     """saliency_mgd_loss (loss.py:335-360): mask = highest-score tokens; mean-MSE * 4."""
     x = _align(s_feats[-1], heads["align.weight"], heads["align.bias"])
     with torch.no_grad():
         score = saliency_score(method, t_feats[-1], heads)
     mask, _, _ = mask_from_scores(score, len_keep_of(x.shape[1], mask_ratio))
     t = t_feats[-1][:, 2:]
-    return masked_generation_sse(x, mask.to(x.dtype), t, heads) / t.numel() * 4
+    return masked_generation_sse(x, mask.to(x.dtype), t, heads, probe) / t.numel() * 4
 
 
-def curkd_late(s_feats, t_feats, heads, noise) -> torch.Tensor:
+def curkd_late(s_feats, t_feats, heads, noise, probe=None) -> torch.Tensor:
     """curkd_loss epoch>=151 (loss.py:394-420): layer 11, ratio fixed 0.5, sum-MSE * 5e-5/B."""
     x = _align(s_feats[11], heads["curkd_align_last.weight"], heads["curkd_align_last.bias"])
     _, mask, _, _ = random_masking(x, 0.5, noise)
     B = x.shape[0]
-    return masked_generation_sse(x, mask, t_feats[11][:, 2:], heads) / B * 5e-5
+    return masked_generation_sse(x, mask, t_feats[11][:, 2:], heads, probe) / B * 5e-5
 
 
-def vitkd(s_feats, t_feats, heads, noise, alpha_v=0.00003, beta_v=0.000003, lambda_v=0.5) -> torch.Tensor:
+def vitkd(s_feats, t_feats, heads, noise, alpha_v=0.00003, beta_v=0.000003, lambda_v=0.5, probe=None) -> torch.Tensor:
     """vitkd_loss (loss.py:251-311): 2-layer mimic (align2) + masked generation on the last layer."""
     B = s_feats[0].shape[0]
     lr = 0.0
@@ -210,7 +210,7 @@ def vitkd(s_feats, t_feats, heads, noise, alpha_v=0.00003, beta_v=0.000003, lamb
     lr = lr / B * alpha_v
     x = _align(s_feats[-1], heads["align.weight"], heads["align.bias"])
     _, mask, _, _ = random_masking(x, lambda_v, noise)
-    gen = masked_generation_sse(x, mask, t_feats[-1][:, 2:], heads) / B * beta_v / lambda_v
+    gen = masked_generation_sse(x, mask, t_feats[-1][:, 2:], heads, probe) / B * beta_v / lambda_v
     return lr + gen
 
 
@@ -265,7 +265,7 @@ def wass_sinkhorn(s_feats, t_feats, heads, blur: float = 0.05) -> torch.Tensor:
 # --------------------------------------------------------------------------- dispatcher
 def distillation_loss(dtype_: str, outputs, labels, teacher_logits, s_feats, t_feats, heads, args,
                       alpha: float, tau: float, base_kind: str = "soft_target", noise=None,
-                      lrkd_signs=None) -> torch.Tensor:
+                      lrkd_signs=None, probe=None) -> torch.Tensor:
     """DistillationLoss.forward (loss.py:29-242) with the teacher outputs passed in."""
     outputs_kd = None
     if not isinstance(outputs, torch.Tensor):
@@ -281,16 +281,16 @@ def distillation_loss(dtype_: str, outputs, labels, teacher_logits, s_feats, t_f
     elif t == "hard":
         kd = hard_kd(outputs_kd, teacher_logits)
     elif t == "vitkd":
-        return base + vitkd(s_feats, t_feats, heads, noise)
+        return base + vitkd(s_feats, t_feats, heads, noise, probe=probe)
     elif t == "lrkd":
         kd = lrkd(s_feats, t_feats, heads, args.lrkd_rank,
                   (args.lrkd_alpha, args.lrkd_beta, args.lrkd_gamma), lrkd_signs)
     elif t == "curkd":
         if args.current_epoch < 151:
             return base + curkd_hidden(s_feats, t_feats, heads, args.current_epoch)
-        return base + curkd_late(s_feats, t_feats, heads, noise)
+        return base + curkd_late(s_feats, t_feats, heads, noise, probe)
     elif t == "saliency_mgd":
-        return base + saliency_mgd(s_feats, t_feats, heads, args.saliency_mask_ratio, args.saliency_method)
+        return base + saliency_mgd(s_feats, t_feats, heads, args.saliency_mask_ratio, args.saliency_method, probe)
     elif t == "wasskd":
         if args.wasskd_type == "l1":
             w = wass_l1(s_feats, t_feats, heads)
@@ -300,7 +300,7 @@ def distillation_loss(dtype_: str, outputs, labels, teacher_logits, s_feats, t_f
             w = 0.0  # loss.py:186-226: any other value leaves loss_wass = 0.0
         return base + w * 5.0
     elif t == "mgd":
-        return base + mgd(s_feats, t_feats, heads, args.mgd_alpha, args.mgd_mask_ratio, noise)
+        return base + mgd(s_feats, t_feats, heads, args.mgd_alpha, args.mgd_mask_ratio, noise, probe)
     else:
         raise ValueError(f"Invalid distillation type: {dtype_}")
     return base * (1 - alpha) + kd * alpha

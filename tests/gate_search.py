@@ -38,3 +38,32 @@ def best_gate_oracle(eval_fn, ours: dict, tau: float = 3e-5, max_flips: int = 64
         else:
             gate[idx] = 1 - gate[idx]
     return best[0], best[1], int(amb.shape[0]), flipped
+
+
+def case_gate_oracle(name: str, c, tau: float = 3e-5, max_flips: int = 48):
+    """fp64 oracle of golden case `name` compared, gate-aware, with the gradients held by the GPU case `c`
+    (tests.cases.build_case(..., device='cuda') after backward).  Returns (loss, grads, ours, n_amb, n_flip);
+    keys: head parameter names and 's<i>' for student feature i."""
+    from oracle import losses as O
+    from tests.cases import build_case
+    from deltakd_b200 import heads as H
+
+    ours = {k: p.grad.detach().double().cpu() for k, p in H.head_tensors(c.student).items() if p.grad is not None}
+    for i, f in enumerate(c.s_feats):
+        if f is not None and f.grad is not None:
+            ours[f"s{i}"] = f.grad.detach().double().cpu()
+
+    def eval_fn(probe):
+        o = build_case(name, dtype=torch.float64)
+        oh = H.head_tensors(o.student)
+        l = O.distillation_loss(o.kind, o.outputs, o.labels, o.teacher_logits, o.s_feats, o.t_feats, oh, o.args,
+                                o.alpha, o.tau, noise=o.noise, probe=probe)
+        l.backward()
+        g = {k: v.grad for k, v in oh.items() if v.grad is not None}
+        for i, f in enumerate(o.s_feats):
+            if f.grad is not None:
+                g[f"s{i}"] = f.grad
+        return l, g
+
+    loss, grads, n_amb, n_flip = best_gate_oracle(eval_fn, {k: v for k, v in ours.items()}, tau=tau, max_flips=max_flips)
+    return loss, grads, ours, n_amb, n_flip
