@@ -43,6 +43,9 @@ SIGNATURES = {
     "dkd_saliency_selfdiag_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
     "dkd_saliency_selfdiag_score": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _sz, _p]),
     "dkd_saliency_cls_score": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p]),
+    "dkd_lrkd_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i, _i, _i, _i]),
+    "dkd_lrkd_fwdbwd": (_i, [_i, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p,
+                             _p, _sz, _p]),
     "dkd_align_mse_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
 }
 

@@ -395,3 +395,97 @@ def saliency_score_cross(x_query, x_key, q_weight, q_bias, k_weight, k_bias, num
     s = _cls_score(_ptr(xq), xq.stride(0) if B > 1 else D, _ptr(xk), Tk * D, n, B, D, _dtype_code(xk), f32(q_weight), f32(q_bias),
                    f32(k_weight), f32(k_bias), num_heads, 0, xk.device)
     return s.unsqueeze(1)
+
+
+# --------------------------------------------------------------------------- LRKD (low-rank projection matching)
+def _ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[0 if t is None else t.data_ptr() for t in tensors])
+
+
+class _LrkdLayers(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rank, coef, s_off, t_off, n_layers, basis_out, *tensors):
+        s_list = tensors[:n_layers]
+        t_list = tensors[n_layers:2 * n_layers]
+        w_list = tensors[2 * n_layers:3 * n_layers]
+        b_list = tensors[3 * n_layers:4 * n_layers]
+        s0, t0 = s_list[0], t_list[0]
+        dev = s0.device
+        B, Ts, Ds = s0.shape
+        _, Tt, Dt = t0.shape
+        n_tok = Ts - s_off
+        prec = _precision_for(s0)
+        dt = _dtype_code(s0)
+        g_s = [torch.empty_like(s) if ctx.needs_input_grad[6 + i] else None for i, s in enumerate(s_list)]
+        need_w = [ctx.needs_input_grad[6 + 2 * n_layers + i] for i in range(n_layers)]
+        need_b = [b_list[i] is not None and ctx.needs_input_grad[6 + 3 * n_layers + i] for i in range(n_layers)]
+        g_W = [torch.empty_like(w) if (need_w[i] or need_b[i]) else None for i, w in enumerate(w_list)]
+        g_b = [torch.empty_like(b_list[i]) if need_b[i] else None for i in range(n_layers)]
+        loss = torch.zeros((), dtype=torch.float32, device=dev)
+        vk = [torch.empty(rank, Dt, dtype=torch.float32, device=dev) for _ in range(n_layers)] if basis_out is not None else [None] * n_layers
+        sv = [torch.empty(rank, dtype=torch.float32, device=dev) for _ in range(n_layers)] if basis_out is not None else [None] * n_layers
+        sweeps = torch.zeros(n_layers, dtype=torch.int32, device=dev) if basis_out is not None else None
+        nbytes = _lib.lib.dkd_lrkd_workspace_bytes(n_layers, B, n_tok, Ds, Dt, rank, dt, prec)
+        if nbytes == 0:
+            raise ValueError(f"LRKD: unsupported geometry (layers={n_layers}, Dt={Dt})")
+        ws = _scratch(dev, "lrkd", nbytes)
+        coef_arr = (C.c_float * n_layers)(*[float(c) for c in coef])
+        _lib.call("dkd_lrkd_fwdbwd", n_layers, _ptr_array(s_list), _ptr_array(t_list), _ptr_array(w_list), _ptr_array(b_list),
+                  coef_arr, B, Ts, s_off, Tt, t_off, n_tok, Ds, Dt, rank, dt, prec, _ptr_array(g_s), _ptr_array(g_W),
+                  _ptr_array(g_b), _ptr(loss), _ptr_array(vk), _ptr_array(sv), _ptr(sweeps), _ptr(ws), ws.numel(), _stream())
+        if basis_out is not None:
+            basis_out.update(V=vk, S=sv, sweeps=sweeps)
+        ctx.grads = (g_s, [g if need_w[i] else None for i, g in enumerate(g_W)], g_b)
+        ctx.n_layers = n_layers
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        n = ctx.n_layers
+        gs, gw, gb = ctx.grads
+        ctx.grads = None
+        _rescale_(grad_out, *gs, *gw, *gb)
+        return (None,) * 6 + (*gs, *([None] * n), *gw, *gb)
+
+
+def lrkd_layers_loss(s_feats, t_feats, linears, rank: int, coef, weight: float = 1.0, s_off: int = 1, t_off: int = 2,
+                     basis_out: dict | None = None):
+    """weight * sum_l coef[l] * mean((T_l V_k - Linear_l(s_l[:, s_off:]))**2), T_l = t_l[:, t_off:] flattened to [B*N, Dt] and
+    V_k its top-`rank` right singular vectors (loss.py:80-103, 314-330: U_k S_k == T V_k).  0-dim fp32.
+    `basis_out` (dict) receives V (list of [rank, Dt]), S (singular values) and the Jacobi sweep counts."""
+    n = len(linears)
+    s_list, t_list, w_list, b_list = [], [], [], []
+    for s, t, lin in zip(s_feats, t_feats, linears):
+        _check_feature_pair(s, t, s_off, t_off)
+        if lin.weight.shape[0] != rank:
+            raise ValueError(f"LRKD head projects to {lin.weight.shape[0]} dims but rank is {rank}")
+        t = t.detach()
+        if t.dtype != s.dtype:
+            t = t.to(s.dtype)
+        s_list.append(s.contiguous())
+        t_list.append(t.contiguous())
+        w_list.append(lin.weight.float().contiguous() if lin.weight.dtype != torch.float32 else lin.weight.contiguous())
+        b_list.append(None if lin.bias is None else lin.bias.float().contiguous())
+    coef = [float(c) * float(weight) for c in coef]
+    return _LrkdLayers.apply(rank, coef, s_off, t_off, n, basis_out, *s_list, *t_list, *w_list, *b_list)
+
+
+class _FixedHead:
+    def __init__(self, weight):
+        self.weight, self.bias = weight, None
+
+
+def lrkd_projected_loss(teacher_features, student_features, rank: int, coef):
+    """The reference's free function lrkd_loss (loss.py:314-330) on ALREADY projected student features [B, N, rank]
+    and sliced teacher features [B, N, Dt].  Runs the same fused kernels with an identity head: the projected
+    features are zero-padded to the kernel's student width (192) and matched through W = [I_rank | 0]."""
+    import torch.nn.functional as F
+    s_pad, heads = [], []
+    for s in student_features:
+        if s.shape[-1] != rank or rank > 192:
+            raise ValueError(f"projected student features must be [B, N, rank<=192], got {tuple(s.shape)} for rank {rank}")
+        s_pad.append(F.pad(s, (0, 192 - rank)))
+        w = torch.zeros(rank, 192, dtype=torch.float32, device=s.device)
+        w[:, :rank] = torch.eye(rank, device=s.device)
+        heads.append(_FixedHead(w))
+    return lrkd_layers_loss(s_pad, list(teacher_features), heads, rank, coef, s_off=0, t_off=0)

@@ -112,9 +112,10 @@ class DistillationLoss(nn.Module):
         if kind == 'lrkd':
             s_sel = [student_features[0], student_features[1], student_features[-1]]
             t_sel = [teacher_features[0], teacher_features[1], teacher_features[11]]
-            kd = Fn.lrkd_layers_loss(s_sel, t_sel, student.align, args.lrkd_rank,
-                                     (args.lrkd_alpha, args.lrkd_beta, args.lrkd_gamma))
-            return base_loss * (1 - self.alpha) + kd * self.alpha
+            # the mixing weight alpha (loss.py:241) is folded into the kernels: no rescale pass in backward
+            kd_a = Fn.lrkd_layers_loss(s_sel, t_sel, list(student.align), args.lrkd_rank,
+                                       (args.lrkd_alpha, args.lrkd_beta, args.lrkd_gamma), weight=self.alpha)
+            return base_loss * (1 - self.alpha) + kd_a
         if kind == 'curkd':
             return base_loss + curkd_loss(student, student_features, teacher_features, args)
         if kind == 'saliency_mgd':

@@ -184,6 +184,30 @@ DKD_API int dkd_saliency_cls_score(const void* xq, int64_t xq_stride, const void
                                    int64_t B, int D, int dtype, const float* Wq, const float* bq, const float* Wk,
                                    const float* bk, int num_heads, int query_is_key, float* score, dkd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LRKD low-rank projection matching, all selected layers, forward + backward:
+ *     T_l = t[l][:, t_off:, :].reshape(M, Dt) ;  V_k = top-`rank` right singular vectors of T_l ;  A = T_l V_k
+ *     s'  = s[l][:, s_off:, :] W[l]^T + bias[l]            (W[l] : [rank, Ds])
+ *     *loss += coef[l] / (M * rank) * sum((A - s')^2)      (accumulates; coef is a HOST array)
+ * plus g_s[l], g_W[l], g_b[l] (overwritten; any may be NULL).  Replaces model/loss.py:80-103 and lrkd_loss
+ * (:314-330): `U,S,_ = torch.linalg.svd(T); A = U[:, :k] diag(S[:k])` (= T V_k), `MSELoss(mean)` against the projected
+ * student, weighted by lrkd_alpha/beta/gamma, and their backward.  The tall SVD is replaced by the fp64 Jacobi
+ * eigen-decomposition of the Dt x Dt Gram matrix T^T T (tcgen05, fp32-exact split operands, fp64 reduction).
+ * The sign of each singular vector is arbitrary in any SVD; here the largest-magnitude component of every v is
+ * positive.  Vk_out[l] (fp32 [rank, Dt]) and S_out[l] (fp32 [rank], singular values) are optional outputs for
+ * sign alignment and inspection; sweeps_out (int[n_layers], device) receives the Jacobi sweep counts.
+ * s, t, W, bias, g_*, Vk_out, S_out are HOST arrays of n_layers device pointers (n_layers <= 8).
+ * Built for Ds = 192, Dt = 384, rank <= 128.  The eigensolver is one cooperative launch (needs 24*n_layers
+ * co-resident CTAs).
+ */
+DKD_API size_t dkd_lrkd_workspace_bytes(int n_layers, int64_t B, int n_tok, int Ds, int Dt, int rank, int dtype,
+                                        int precision);
+DKD_API int dkd_lrkd_fwdbwd(int n_layers, const void* const* s, const void* const* t, const float* const* W,
+                            const float* const* bias, const float* coef, int64_t B, int Ts, int s_off, int Tt, int t_off,
+                            int n_tok, int Ds, int Dt, int rank, int dtype, int precision, void* const* g_s,
+                            float* const* g_W, float* const* g_b, float* loss, float* const* Vk_out, float* const* S_out,
+                            int* sweeps_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,7 +137,7 @@ def _align(s: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def curkd_hidden(s_feats, t_feats, heads, epoch: int) -> torch.Tensor:
     """curkd_loss early/mid (loss.py:376-393): sum-MSE over the selected layers * 4e-5/(nL*B)."""
-    B = s_feats[0].shape[0]
+    B = next(f for f in s_feats if f is not None).shape[0]
     if epoch < 100:
         layers, name, off = range(3), "curkd_align_early", 0
     else:

@@ -94,7 +94,7 @@ def test_generation_shapes_and_modes(B, ratio, mode):
             return l, g
 
         tau = 3e-5 if mode == "bf16x3" else 3e-2
-        ref, grads, n_amb, n_flip = best_gate_oracle(eval_fn, ours, tau=tau, max_flips=48 if mode == "bf16x3" else 0)
+        ref, grads, n_amb, n_flip = best_gate_oracle(eval_fn, ours, tau=tau, max_flips=160 if mode == "bf16x3" else 0)
         lt, gt = (1e-5, 1e-4) if mode == "bf16x3" else (5e-3, 6e-2)   # one bf16 pass through two K=3456 convolutions
         assert abs(loss.item() - ref.item()) <= lt * abs(ref.item()), (loss.item(), ref.item())
         for k in ours:
