@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16);
       float* drow = p.ep.D + it.d_off + (size_t)row * p.ep.ldd;
-      const bool row_ok = row < p.ep.rows_valid;
+      const bool row_ok = row < p.ep.rows_valid && row < it.rows;
 #pragma unroll 1
       for (int c0 = 0; c0 < Cfg::NB_DATA; c0 += 32) {
         float v[32];
@@ -192,6 +192,7 @@ struct NtItem {
   int64_t d_off;     // element offset of the tile's (0,0) in D
   int dcol_off;      // offset into Dcol, or -1
   int aux;           // loader specific (e.g. filter tap)
+  int rows = 128;    // output rows of this item's tile that exist (<= 128)
 };
 
 // Plain loader: A = planes [P][R][NA_total], B = planes [P][R][NB_total], 3-D maps {cols, rows, planes}, box {64, KROWS, 1}.

@@ -109,4 +109,4 @@ def test_wass_l1_sorted_properties(B, dtype):
     t2 = torch.zeros_like(t)
     t2[:, 2:] = torch.cat([s[:, 1:], s[:, 1:]], dim=-1)[:, torch.randperm(196, generator=g).cuda()]
     zero = Fn.wass_l1_loss([s], [t2], [lin], weight=1.0).item()
-    assert abs(zero) <= (1e-6 if dtype == torch.float32 else 1e-2) * max(1.0, abs(base))
+    assert abs(zero) <= (2e-5 if dtype == torch.float32 else 1e-2) * max(1.0, abs(base))  # bf16x3 identity: 2^-16
