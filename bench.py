@@ -333,8 +333,83 @@ class WassL1(FeatureKD):
         return Fn.wass_l1_loss(ds["s"][:3], ds["t"][:3], list(self.student.align_wasskd), weight=5.0)
 
 
+class WassSinkhorn(FeatureKD):
+    """configs[4] (sinkhorn variant): debiased Sinkhorn divergence per (sample, layer), layers 0-2, B=512 per GPU.
+    On-chip bound (MUFU ex2 + eps-step latency): the HBM fraction is reported for completeness, the meaningful
+    figure is `exp_per_s` against 16 ex2/clk/SM x 148 SMs."""
+    name = "wasskd_sinkhorn_b512_f32"
+    kind, layers, B, cpu_B = "wasskd", (0, 1, 2), 512, 1
+    default_steps = 5
+    args_kw = dict(wasskd_type="sinkhorn")
+    feat_kw = dict(scale=0.5, t_shift=0.1)
+    dominant = "dkd_wass_sinkhorn_fwdbwd (sinkhorn_kernel<xy>, <xx/yy>: cost matrix in shared memory)"
+    N_EPS = 13  # diameter ~59 at this scale (SURVEY 8d)
+
+    def algorithmic_flops(self):
+        return len(self.layers) * self.B * (3 * 2.0 * 196 * 196 * 384 + 2 * 2.0 * 196 * 196 * 384 + 3 * 2.0 * 196 * 192 * 384)
+
+    def extra_roofline(self, k_ms):
+        exps = len(self.layers) * self.B * (self.N_EPS + 2) * 4 * 196 * 196 * 1.0
+        peak = 16 * 148 * 1.965e9
+        return {"exp_per_s": exps / (k_ms * 1e-3), "mufu_peak_exp_per_s": peak, "mufu_frac": exps / (k_ms * 1e-3) / peak,
+                "note": "bound is MUFU ex2 / eps-step latency (on-chip); hbm frac is n/a by construction"}
+
+    def feature_loss(self, L, ds):
+        from deltakd_b200 import functional as Fn
+        return Fn.wass_sinkhorn_loss(ds["s"][:3], ds["t"][:3], list(self.student.align_wasskd), weight=5.0)
+
+
+class LRKD(FeatureKD):
+    """configs[4] (LRKD): rank-64 projection matching on layers (0, 1, 11), B=512 per GPU (global 1024 at 2 GPUs)."""
+    name = "lrkd_r64_b512_f32"
+    kind, layers, B, cpu_B = "lrkd", (0, 1, 11), 512, 32
+    args_kw = dict(lrkd_rank=64, lrkd_alpha=0.2, lrkd_beta=0.2, lrkd_gamma=0.2)
+    dominant = "dkd_lrkd_fwdbwd (teacher planes, tcgen05 Gram, fp64 Jacobi eigensolver, fused projection GEMMs)"
+
+    def algorithmic_bytes(self):  # per layer: T read twice (Gram, projection) + s + g_s  (SURVEY 8d cfg5)
+        return len(self.layers) * self.B * 196 * (2 * 384 + 192 + 192) * 4
+
+    def algorithmic_flops(self):
+        M = self.B * 196
+        return len(self.layers) * (2.0 * M * 384 * 384 + 2.0 * M * 384 * 64 + 3 * 2.0 * M * 192 * 64)
+
+    def feature_loss(self, L, ds):
+        from deltakd_b200 import functional as Fn
+        a = self.args
+        return Fn.lrkd_layers_loss([ds["s"][0], ds["s"][1], ds["s"][11]], [ds["t"][0], ds["t"][1], ds["t"][11]],
+                                   list(self.student.align), a.lrkd_rank, (a.lrkd_alpha, a.lrkd_beta, a.lrkd_gamma), weight=0.1)
+
+
+class SaliencyMGD(MGD):
+    """configs[3] (saliency variant): saliency-MGD method 1 (self-attention diagonal), ratio 0.5, B=512."""
+    name = "saliency_mgd_m1_b512_f32"
+    kind = "saliency_mgd"
+    args_kw = dict(saliency_method=1, saliency_mask_ratio=0.5)
+
+    def algorithmic_flops(self):
+        M = self.B * 196
+        return super().algorithmic_flops() + 2.0 * M * 384 * 768 + 2.0 * self.B * 8 * 196 * 196 * 48
+
+    def feature_loss(self, L, ds):
+        return L.saliency_mgd_loss(self.student, ds["s"], ds["t"], self.args)
+
+
+class CurKDEarlyBf16(CurKDEarly):
+    """CurKD early with bf16 activations (one tcgen05 pass): tensor-pipe-bound form of configs[2]."""
+    name = "curkd_early_3layers_b512_bf16"
+    dtype = "bf16"
+    tdtype = torch.bfloat16
+
+
+class MGDBf16(MGD):
+    """MGD with bf16 activations (one tcgen05 pass per GEMM)."""
+    name = "mgd_b512_bf16"
+    dtype = "bf16"
+    tdtype = torch.bfloat16
+
+
 HEADLINE = LogitKD
-EXTRAS = (CurKDEarly, CurKDMid, MGD, WassL1)
+EXTRAS = (CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16, SaliencyMGD, LRKD, WassL1, WassSinkhorn)
 WORKLOADS = {w.name: w for w in (HEADLINE,) + EXTRAS}
 
 
@@ -475,6 +550,8 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
     }
     if w.bound == "hbm" and w.algorithmic_flops():
         res["roofline"]["algorithmic_flops"] = w.algorithmic_flops()
+    if hasattr(w, "extra_roofline"):
+        res["roofline"].update(w.extra_roofline(k_ms))
     if with_cpu:
         res["cpu_baseline"] = cpu_baseline(w, budget_s=12.0 if isinstance(w, LogitKD) else 6.0)
     del dsets, host
@@ -528,7 +605,12 @@ def main():
     extras = []
     if not args.no_extras and w_cls is HEADLINE:
         for cls in EXTRAS:
-            r, win = measure(cls(dev, rank), min(args.steps, cls.default_steps), W, world, barrier, allmax, pk, with_cpu)
+            try:
+                r, win = measure(cls(dev, rank), min(args.steps, cls.default_steps), W, world, barrier, allmax, pk, with_cpu)
+            except Exception as e:  # one failing extra must not cost the headline line; it is reported, not hidden
+                r, win = {"workload": cls.name, "error": f"{type(e).__name__}: {e}"[:400]}, []
+                torch.cuda.synchronize()
+                torch.cuda.empty_cache()
             extras.append(r)
             windows += win
 

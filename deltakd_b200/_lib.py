@@ -40,6 +40,8 @@ SIGNATURES = {
     "dkd_masked_generation_fwdbwd": (_i, [_p] * 10 + [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _f] + [_p] * 10 + [_sz, _p]),
     "dkd_wass_l1_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_wass_l1_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "dkd_wass_sinkhorn_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
+    "dkd_wass_sinkhorn_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "dkd_saliency_selfdiag_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
     "dkd_saliency_selfdiag_score": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _sz, _p]),
     "dkd_saliency_cls_score": (_i, [_p, _i64, _p, _i64, _i, _i64, _i, _i, _p, _p, _p, _p, _i, _i, _p, _p]),

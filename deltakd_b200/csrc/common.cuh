@@ -106,6 +106,19 @@ template <typename T, int VEC> struct Vec {
   }
 };
 
+// fp32 x[32] -> bf16 hi (and lo = x - hi) planes, 64 contiguous bytes each
+__device__ __forceinline__ void store_planes32(__nv_bfloat16* hi_ptr, int64_t plane_stride, int planes, float (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
+  if (planes == 2) {
+    float lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) lo[j] = x[j] - __bfloat162float(__float2bfloat16_rn(x[j]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + plane_stride + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
+  }
+}
+
 // ---- reductions ----------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -4,19 +4,6 @@
 
 namespace dkd {
 
-// fp32 x[32] -> bf16 hi (and lo = x - hi) planes, 64 contiguous bytes each
-__device__ __forceinline__ void store_planes32(__nv_bfloat16* hi_ptr, int64_t plane_stride, int planes, float (&x)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
-  if (planes == 2) {
-    float lo[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) lo[j] = x[j] - __bfloat162float(__float2bfloat16_rn(x[j]));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + plane_stride + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
-  }
-}
-
 // 32 consecutive activations (fp32 or bf16 storage) -> fp32 registers
 __device__ __forceinline__ void load_act32(const void* base, int64_t elem_off, int is_bf16, float (&x)[32]) {
   if (is_bf16) {

@@ -15,8 +15,9 @@
 
 namespace dkd {
 
-template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64>
+template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64, bool A_KMAJOR_ = false>
 struct GemmNtCfg {
+  static constexpr bool A_KMAJOR = A_KMAJOR_;       // A tile is [128 rows x 64 k] K-major (one box) instead of two MN-major boxes
   static constexpr int NA = 128;                      // UMMA M
   static constexpr int NB_BOXES = NB_BOXES_;          // 64-column boxes of B data
   static constexpr bool ONES = ONES_;
@@ -37,6 +38,7 @@ struct GemmNtCfg {
   static_assert(N0_ % 16 == 0 && N0_ <= 256 && N1_ % 16 == 0 && N1_ <= 256 && (N1_ == 0 || N0_ % 64 == 0), "UMMA N split");
   static_assert(KROWS_ % 16 == 0 && BOX_BYTES % 1024 == 0, "K rows per stage");
   static_assert(NB <= 512 && SMEM <= 227 * 1024, "resources");
+  static_assert(!A_KMAJOR_ || KROWS_ == 64, "K-major A tiles are 128 x 64");
 };
 
 struct NtEpilogueParams {
@@ -46,6 +48,9 @@ struct NtEpilogueParams {
   float alpha = 1.f;
   int store = 0;          // 1: the tile is written with plain stores (each item owns its output, e.g. per-split partials)
   int rows_valid = 128;   // output rows of the 128-row tile that exist (A narrower than 128 columns)
+  __nv_bfloat16* Dplanes = nullptr;  // if set: the tile is written as bf16 hi(/lo) planes here instead of fp32 D
+  int64_t plane_stride = 0;
+  int n_planes = 0;
 };
 
 // Loader policy interface:
@@ -105,8 +110,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc0 = make_idesc_bf16(128, Cfg::N0, MAJOR_MN, MAJOR_MN);
-      constexpr uint32_t idesc1 = make_idesc_bf16(128, Cfg::N1 > 0 ? Cfg::N1 : 16, MAJOR_MN, MAJOR_MN);
+      constexpr uint32_t a_major = Cfg::A_KMAJOR ? MAJOR_K : MAJOR_MN;
+      constexpr uint32_t idesc0 = make_idesc_bf16(128, Cfg::N0, a_major, MAJOR_MN);
+      constexpr uint32_t idesc1 = make_idesc_bf16(128, Cfg::N1 > 0 ? Cfg::N1 : 16, a_major, MAJOR_MN);
       int s = 0; uint32_t ph = 0; uint32_t aph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         typename Loader::Item it;
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           const uint32_t b_addr = smem_u32(sB + (size_t)s * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < Cfg::KSTEPS; ++k) {  // UMMA_K = 16 rows = 2 groups of 8 rows = 2048 B
-            const uint64_t da = mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
+            const uint64_t da = Cfg::A_KMAJOR ? kmajor_desc(a_addr + k * 32) : mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
             umma_bf16(tmem_base, da, mnmajor_desc(b_addr + k * 2048, Cfg::BOX_BYTES), idesc0, (kit | k) != 0 ? 1u : 0u);
             if constexpr (Cfg::N1 > 0)
               umma_bf16(tmem_base + Cfg::N0, da, mnmajor_desc(b_addr + (Cfg::N0 / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES),
@@ -154,7 +160,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
         tmem_ld32(t_acc + c0, v);
         tmem_ld_wait();
         if (!row_ok) continue;
-        if (p.ep.store) {
+        if (p.ep.Dplanes) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.ep.alpha;
+          store_planes32(p.ep.Dplanes + it.d_off + (size_t)row * p.ep.ldd + c0, p.ep.plane_stride, p.ep.n_planes, v);
+        } else if (p.ep.store) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(drow + c0 + j) =

@@ -1,0 +1,535 @@
+// WassKD 'sinkhorn' term: debiased Sinkhorn divergence between the 196 aligned student tokens and the 196 teacher
+// tokens of every (sample, layer) pair.
+// Reference: model/loss.py:200-225 — a Python loop of B x 3 calls of geomloss.SamplesLoss("sinkhorn", blur=0.05)
+// (p = 2, scaling = 0.5, debias, uniform weights, tensorized backend), each with a host read-back of the diameter,
+// and its autograd backward.  geomloss is an unlisted, absent third-party dependency: the algorithm follows
+// upstream geomloss 0.2.x as restated in oracle/sinkhorn.py (PARITY UNPINNED).
+//
+// Per layer, all on `stream`, no host read-back (the eps schedule is built on the device):
+//   1-3. a = S W^T + b (tcgen05, fp32 rows) as in wass_l1.cu
+//   4.   x = a, y = t[:, t_off:] -> bf16 hi/lo planes; row square norms; per pair: bounding-box diameter -> eps ladder
+//   5.   cost matrices C_xy, C_xx, C_yy = 0.5(|u|^2 + |v|^2) - u.v : batched tcgen05 GEMMs (bf16x3), one 128 x 208
+//        TMEM tile per (pair, matrix, half), written with a 204-float row pitch (the shared-memory image)
+//   6.   Sinkhorn loops, cost matrix resident in shared memory (one bulk copy), potentials in registers:
+//        xy kernel — one CTA per pair, a thread per row (f_ba) and a thread per column (g_ab) of C_xy;
+//        sym kernel — one CTA per (pair, xx | yy), a thread per row.  Softmins are base-2 log-sum-exps
+//        (two passes: max, then MUFU ex2).  The last (extrapolation) step also emits the transport plans
+//        P = softmax_j(h_b - C_xy/eps), Q = softmax_j(h_a - C_xx/eps) as bf16 hi/lo planes.
+//   7.   g_a = scale/N (Q x - P y): batched tcgen05 GEMM (K-major plans x MN-major points), written as planes
+//   8-9. g_s = g_a W, g_W = g_a^T s, g_b = g_a^T 1 (align_ops.cuh)
+// Bound: MUFU ex2 throughput and the eps-step latency (on-chip); HBM traffic is hidden behind it.
+#include "align_ops.cuh"
+
+namespace dkd {
+namespace {
+
+constexpr int kTok = 196;                   // points per cloud (14 x 14 patch tokens)
+constexpr int kD = 384;                     // teacher width
+constexpr int kLD = 204;                    // cost-matrix row pitch in floats: 16-byte rows, conflict-free LDS.128 per row-thread
+constexpr int kCostBytes = kTok * kLD * 4;  // 159 936
+constexpr int kLDP = 208;                   // plan row pitch in bf16 (416 B)
+constexpr int kMaxEps = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ 4. norms, diameter, eps ladder
+struct PrepParams {
+  const float* A;     // [B*196, 384] aligned student
+  const void* t;      // teacher [B, Tt, 384]
+  float *nx, *ny;     // [B*196]
+  float* eps;         // [B][kMaxEps]
+  int* n_eps;         // [B]
+  int Tt, t_off, t_is_bf16;
+  float blur, scaling;
+};
+
+__device__ __forceinline__ float ld_t(const void* t, int64_t idx, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(t)[idx]) : reinterpret_cast<const float*>(t)[idx];
+}
+
+// one CTA per pair, thread = coordinate: bounding box of x u y -> diameter -> eps list (geomloss epsilon_schedule)
+__global__ void __launch_bounds__(kD) sinkhorn_prep_kernel(PrepParams p) {
+  const int b = blockIdx.x, d = threadIdx.x;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = 0; i < kTok; ++i) {
+    const float a = p.A[((int64_t)b * kTok + i) * kD + d];
+    const float y = ld_t(p.t, ((int64_t)b * p.Tt + p.t_off + i) * kD + d, p.t_is_bf16);
+    mn = fminf(mn, fminf(a, y));
+    mx = fmaxf(mx, fmaxf(a, y));
+  }
+  __shared__ double red[kD / 32];
+  double r = (double)(mx - mn) * (double)(mx - mn);
+  r = warp_sum(r);
+  if ((d & 31) == 0) red[d >> 5] = r;
+  __syncthreads();
+  if (d == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kD / 32; ++w) s += red[w];
+    const double diam = (double)(float)sqrt(s);   // torch: fp32 .norm().item()
+    float* e = p.eps + (size_t)b * kMaxEps;
+    const double start = 2.0 * log(diam), stop = 2.0 * log((double)p.blur), step = 2.0 * log((double)p.scaling);
+    int n = (int)ceil((stop - start) / step);      // len(np.arange(start, stop, step))
+    if (!(n > 0)) n = 0;
+    if (n > kMaxEps - 2) n = kMaxEps - 2;
+    e[0] = (float)(diam * diam);
+    for (int k = 0; k < n; ++k) e[1 + k] = (float)exp(start + k * step);
+    e[1 + n] = p.blur * p.blur;
+    p.n_eps[b] = n + 2;
+  }
+}
+
+// warp per row: square norms of the aligned student rows and of the teacher rows
+__global__ void __launch_bounds__(256) sinkhorn_norms_kernel(PrepParams p, int64_t M) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int64_t b = row / kTok, i = row - b * kTok;
+  float sx = 0.f, sy = 0.f;
+  for (int c = lane * 4; c < kD; c += 128) {
+    float v[4];
+    Vec<float, 4>::load(p.A + row * kD + c, v);
+    sx += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+    const int64_t toff = (b * p.Tt + p.t_off + i) * kD + c;
+    if (p.t_is_bf16) Vec<__nv_bfloat16, 4>::load(reinterpret_cast<const __nv_bfloat16*>(p.t) + toff, v);
+    else Vec<float, 4>::load(reinterpret_cast<const float*>(p.t) + toff, v);
+    sy += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy);
+  if (lane == 0) { p.nx[row] = sx; p.ny[row] = sy; }
+}
+
+// ------------------------------------------------------------------ 5. cost matrices (gemm_tn policies)
+// tile index mt = (pair*3 + which)*2 + half ; which: 0 = C_xy (x rows, y cols), 1 = C_xx, 2 = C_yy
+using CostCfg = GemmCfg<208, 1, 4, 2>;
+
+struct CostLoaderParams {
+  CUtensorMap tmXa, tmXb, tmYa, tmYb;   // 4-D {384, 196, B, planes}; a: box {64,128,1,1}, b: box {64,208,1,1}
+  int nterms;
+};
+struct CostLoader {
+  using Params = CostLoaderParams;
+  static constexpr uint32_t TX_BYTES = CostCfg::STAGE_BYTES;
+  static __device__ __forceinline__ int num_k_iters(const Params& p) { return (kD / 64) * p.nterms; }
+  static __device__ __forceinline__ void prefetch(const Params& p) {
+    sm100::tma_prefetch_desc(&p.tmXa); sm100::tma_prefetch_desc(&p.tmXb);
+    sm100::tma_prefetch_desc(&p.tmYa); sm100::tma_prefetch_desc(&p.tmYb);
+  }
+  static __device__ __forceinline__ void issue(const Params& p, int kit, int mt, int, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
+    const int term = kit / (kD / 64), kb = kit - term * (kD / 64);
+    int pa, pb;
+    term_planes(term, p.nterms, pa, pb);
+    const int half = mt & 1, which = (mt >> 1) % 3, pair = mt / 6;
+    sm100::tma_load_4d(sA, which == 2 ? &p.tmYa : &p.tmXa, bar, kb * 64, half * 128, pair, pa);
+    sm100::tma_load_4d(sB, which == 1 ? &p.tmXb : &p.tmYb, bar, kb * 64, 0, pair, pb);
+  }
+};
+
+struct CostEpiParams {
+  const float *nx, *ny;
+  float* C;   // [pairs][3][196][kLD]
+};
+struct CostEpi {
+  using Params = CostEpiParams;
+  struct State {};
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int, int row_in_tile, uint32_t t_acc) {
+    const int mt = m0 >> 7;
+    const int half = mt & 1, which = (mt >> 1) % 3, pair = mt / 6;
+    const int i = half * 128 + row_in_tile;
+    const bool live = i < kTok;
+    const float* na = (which == 2 ? p.ny : p.nx) + (size_t)pair * kTok;
+    const float* nb = (which == 1 ? p.nx : p.ny) + (size_t)pair * kTok;
+    const float ni = live ? __ldg(na + i) : 0.f;
+    float* out = p.C + ((size_t)(pair * 3 + which) * kTok + (live ? i : 0)) * kLD;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 192; c0 += 32) {
+      float v[32];
+      sm100::tmem_ld32(t_acc + c0, v);
+      sm100::tmem_ld_wait();
+      if (!live) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 n4 = __ldg(reinterpret_cast<const float4*>(nb + c0 + j));
+        *reinterpret_cast<float4*>(out + c0 + j) = make_float4(0.5f * (ni + n4.x) - v[j], 0.5f * (ni + n4.y) - v[j + 1],
+                                                               0.5f * (ni + n4.z) - v[j + 2], 0.5f * (ni + n4.w) - v[j + 3]);
+      }
+    }
+    float v[32];
+    sm100::tmem_ld32(t_acc + 176, v);   // columns 176..207: the last four real ones are v[16..19]
+    sm100::tmem_ld_wait();
+    if (live) {
+      const float4 n4 = __ldg(reinterpret_cast<const float4*>(nb + 192));
+      *reinterpret_cast<float4*>(out + 192) = make_float4(0.5f * (ni + n4.x) - v[16], 0.5f * (ni + n4.y) - v[17],
+                                                          0.5f * (ni + n4.z) - v[18], 0.5f * (ni + n4.w) - v[19]);
+    }
+  }
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+};
+
+// ------------------------------------------------------------------ 6. Sinkhorn loops
+struct SinkParams {
+  const float* C;          // [pairs][3][196][kLD]
+  const float* eps;        // [pairs][kMaxEps]
+  const int* n_eps;        // [pairs]
+  __nv_bfloat16* plans;    // [2: Q, -P][planes = 2][pairs][196][kLDP]
+  double* partials;        // [pairs*3]
+  int pairs, write_plans;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// bulk copy of one cost matrix into shared memory (thread 0 issues, everybody waits)
+__device__ __forceinline__ void load_cost(float* sC, const float* gC, uint64_t* bar) {
+  using namespace sm100;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar, kCostBytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sC)),
+                 "l"(gC), "r"(kCostBytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+// base-2 log-sum-exp over row i:  log2 sum_j 2^(h[j] - C[i][j]*c2); returns it and (optionally) leaves max / sum
+__device__ __forceinline__ float lse2_row(const float* __restrict__ crow, const float* __restrict__ h, float c2, float& m_out, float& s_out) {
+  const float4* c4 = reinterpret_cast<const float4*>(crow);
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 7
+  for (int k = 0; k < kTok / 4; ++k) {
+    const float4 c = c4[k], hh = h4[k];
+    m0 = fmaxf(m0, fmaf(-c.x, c2, hh.x)); m1 = fmaxf(m1, fmaf(-c.y, c2, hh.y));
+    m2 = fmaxf(m2, fmaf(-c.z, c2, hh.z)); m3 = fmaxf(m3, fmaf(-c.w, c2, hh.w));
+  }
+  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 7
+  for (int k = 0; k < kTok / 4; ++k) {
+    const float4 c = c4[k], hh = h4[k];
+    s0 += ex2f(fmaf(-c.x, c2, hh.x) - m); s1 += ex2f(fmaf(-c.y, c2, hh.y) - m);
+    s2 += ex2f(fmaf(-c.z, c2, hh.z) - m); s3 += ex2f(fmaf(-c.w, c2, hh.w) - m);
+  }
+  const float s = (s0 + s1) + (s2 + s3);
+  m_out = m; s_out = s;
+  return m + __log2f(s);
+}
+
+// ... and over column j (stride kLD; consecutive threads -> consecutive banks)
+__device__ __forceinline__ float lse2_col(const float* __restrict__ ccol, const float* __restrict__ h, float c2) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 7
+  for (int i = 0; i < kTok; i += 4) {
+    m0 = fmaxf(m0, fmaf(-ccol[(i + 0) * kLD], c2, h[i + 0])); m1 = fmaxf(m1, fmaf(-ccol[(i + 1) * kLD], c2, h[i + 1]));
+    m2 = fmaxf(m2, fmaf(-ccol[(i + 2) * kLD], c2, h[i + 2])); m3 = fmaxf(m3, fmaf(-ccol[(i + 3) * kLD], c2, h[i + 3]));
+  }
+  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 7
+  for (int i = 0; i < kTok; i += 4) {
+    s0 += ex2f(fmaf(-ccol[(i + 0) * kLD], c2, h[i + 0]) - m); s1 += ex2f(fmaf(-ccol[(i + 1) * kLD], c2, h[i + 1]) - m);
+    s2 += ex2f(fmaf(-ccol[(i + 2) * kLD], c2, h[i + 2]) - m); s3 += ex2f(fmaf(-ccol[(i + 3) * kLD], c2, h[i + 3]) - m);
+  }
+  return m + __log2f((s0 + s1) + (s2 + s3));
+}
+
+// plan row i:  sign * 2^(h[j] - C[i][j]*c2 - m) / s  as bf16 hi / lo, 4 entries (8 bytes) per store
+__device__ __forceinline__ void write_plan_row(const float* __restrict__ crow, const float* __restrict__ h, float c2, float m, float s,
+                                               float sign, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  const float4* c4 = reinterpret_cast<const float4*>(crow);
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float inv = sign / s;
+#pragma unroll 7
+  for (int k = 0; k < kTok / 4; ++k) {
+    const float4 c = c4[k], hh = h4[k];
+    float v[4], r[4];
+    v[0] = inv * ex2f(fmaf(-c.x, c2, hh.x) - m); v[1] = inv * ex2f(fmaf(-c.y, c2, hh.y) - m);
+    v[2] = inv * ex2f(fmaf(-c.z, c2, hh.z) - m); v[3] = inv * ex2f(fmaf(-c.w, c2, hh.w) - m);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = v[q] - __bfloat162float(__float2bfloat16_rn(v[q]));
+    Vec<__nv_bfloat16, 4>::store(hi + 4 * k, v);
+    Vec<__nv_bfloat16, 4>::store(lo + 4 * k, r);
+  }
+}
+
+constexpr int kRoleThreads = 224;   // 7 warps per role, 196 of them active
+constexpr size_t kSinkSmem = (size_t)kCostBytes + 4 * kTok * sizeof(float) + 64;
+
+// Step schedule (geomloss sinkhorn_loop): step -1 initialises the potentials at eps[0] from the log-weights alone,
+// steps 0..n-1 average (symmetric update) at eps[k], step n is the final extrapolation at eps[n-1] (plain assignment).
+template <bool XY>
+__global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kRoleThreads, 1) sinkhorn_kernel(SinkParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  float* sC = reinterpret_cast<float*>(smem_raw);
+  float* hR = sC + kTok * kLD;            // [2][196] : h over columns j, read by the row threads
+  float* hC = hR + 2 * kTok;              // [2][196] : h over rows i, read by the column threads (xy only)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(hC + 2 * kTok);
+  __shared__ double red[2 * kRoleThreads / 32];
+
+  const int pair = XY ? blockIdx.x : blockIdx.x >> 1;
+  const int which = XY ? 0 : 1 + (blockIdx.x & 1);
+  load_cost(sC, p.C + (size_t)(pair * 3 + which) * kTok * kLD, bar);
+
+  const int n = p.n_eps[pair];
+  const float* eps_list = p.eps + (size_t)pair * kMaxEps;
+  const bool is_col = XY && threadIdx.x >= kRoleThreads;
+  const int idx = is_col ? threadIdx.x - kRoleThreads : threadIdx.x;   // row i or column j
+  const bool active = idx < kTok;
+  const float logw = -__logf((float)kTok);
+  float pot = 0.f;            // f_ba[i] / g_ab[j] (xy) or f_aa[i] / g_bb[i] (sym)
+  float m_fin = 0.f, s_fin = 1.f, c2_fin = 0.f;
+
+  for (int step = -1; step <= n; ++step) {
+    const float eps = eps_list[step < 0 ? 0 : (step < n ? step : n - 1)];
+    const int buf = (step + 1) & 1;
+    // this thread's potential becomes an entry of the h vector the OTHER role reads (same role for the symmetric problems)
+    if (active) {
+      const float hv = (logw + (step < 0 ? 0.f : pot / eps)) * kLog2e;
+      if (XY) (is_col ? hR : hC)[buf * kTok + idx] = hv;
+      else hR[buf * kTok + idx] = hv;
+    }
+    __syncthreads();
+    if (active) {
+      const float c2 = kLog2e / eps;
+      float l2;
+      if (is_col) l2 = lse2_col(sC + idx, hC + buf * kTok, c2);
+      else { l2 = lse2_row(sC + idx * kLD, hR + buf * kTok, c2, m_fin, s_fin); c2_fin = c2; }
+      const float upd = -eps * kLn2 * l2;
+      pot = (step < 0 || step == n) ? upd : 0.5f * (pot + upd);
+    }
+  }
+
+  // divergence partial: xy -> +(sum f_ba + sum g_ab)/N ; xx, yy -> -(sum f)/N
+  double acc = active ? (double)pot : 0.0;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    p.partials[pair * 3 + which] = (XY ? s : -s) / (double)kTok;
+  }
+  // transport plans of the last step (rows only): -P from C_xy, Q from C_xx
+  if (p.write_plans && active && !is_col && which != 2) {
+    const int mat = XY ? 1 : 0;
+    const size_t plane = (size_t)p.pairs * kTok * kLDP;
+    __nv_bfloat16* hi = p.plans + ((size_t)mat * 2 * p.pairs + pair) * kTok * kLDP + (size_t)idx * kLDP;
+    write_plan_row(sC + idx * kLD, hR + ((n + 1) & 1) * kTok, c2_fin, m_fin, s_fin, XY ? -1.f : 1.f, hi, hi + plane);
+  }
+}
+
+// ------------------------------------------------------------------ 7. g_a = alpha (Q x - P y)  (gemm_nt, K-major A)
+using GradCfg = GemmNtCfg<6, false, 256, 128, 3, 64, true>;
+
+struct PlanLoaderParams {
+  CUtensorMap tmPlan;    // 4-D {196 (pitch kLDP), 196, pairs, 4 = mat*2 + plane}, box {64,128,1,1}
+  CUtensorMap tmX, tmY;  // 4-D {384, 196, pairs, 2}, box {64,64,1,1}
+  int pairs;
+};
+struct PlanLoader {
+  using Params = PlanLoaderParams;
+  using Item = NtItem;
+  static constexpr uint32_t TX_BYTES = GradCfg::STAGE_BYTES;
+  static __device__ __forceinline__ int num_items(const Params& p) { return p.pairs * 2; }
+  static __device__ __forceinline__ void prefetch(const Params& p) {
+    sm100::tma_prefetch_desc(&p.tmPlan); sm100::tma_prefetch_desc(&p.tmX); sm100::tma_prefetch_desc(&p.tmY);
+  }
+  static __device__ __forceinline__ void decode(const Params&, int item, Item& it) {
+    const int pair = item >> 1, half = item & 1;
+    it.rb0 = 0; it.rb1 = 8;                 // 4 k-blocks of Q.x then 4 of (-P).y
+    it.a_col0 = half * 128; it.b_col0 = 0;
+    it.d_off = ((int64_t)pair * kTok + half * 128) * kD;
+    it.dcol_off = -1; it.aux = pair;
+    it.rows = half ? kTok - 128 : 128;
+  }
+  static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int nterms, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
+    int pa, pb;
+    term_planes(term, nterms, pa, pb);
+    const int src = rb >> 2, kb = rb & 3;
+    sm100::tma_load_4d(a, &p.tmPlan, bar, kb * 64, it.a_col0, it.aux, src * 2 + pa);
+    const CUtensorMap* mb = src ? &p.tmY : &p.tmX;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sm100::tma_load_4d(b + (size_t)i * GradCfg::BOX_BYTES, mb, bar, i * 64, kb * 64, it.aux, pb);
+  }
+};
+
+struct Workspace {
+  __nv_bfloat16 *S, *Wp, *Wt, *ones, *Xp, *Yp, *plans, *G;
+  float *A, *nx, *ny, *C, *eps;
+  int* n_eps;
+  double* partials;
+  size_t bytes;
+};
+Workspace carve(void* base, int64_t B, int Ds, int Dt, int P) {
+  Workspace w;
+  const int64_t M = B * kTok;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 1024); return reinterpret_cast<char*>(base) + o; };
+  w.S = reinterpret_cast<__nv_bfloat16*>(take((size_t)P * M * Ds * 2));
+  w.Wp = reinterpret_cast<__nv_bfloat16*>(take((size_t)P * Dt * Ds * 2));
+  w.Wt = reinterpret_cast<__nv_bfloat16*>(take((size_t)P * Dt * Ds * 2));
+  w.ones = reinterpret_cast<__nv_bfloat16*>(take((size_t)2 * 64 * 64 * 2));
+  w.A = reinterpret_cast<float*>(take((size_t)M * Dt * 4));
+  w.Xp = reinterpret_cast<__nv_bfloat16*>(take((size_t)2 * M * Dt * 2));
+  w.Yp = reinterpret_cast<__nv_bfloat16*>(take((size_t)2 * M * Dt * 2));
+  w.G = reinterpret_cast<__nv_bfloat16*>(take((size_t)2 * M * Dt * 2));
+  w.nx = reinterpret_cast<float*>(take((size_t)M * 4));
+  w.ny = reinterpret_cast<float*>(take((size_t)M * 4));
+  w.C = reinterpret_cast<float*>(take((size_t)B * 3 * kCostBytes));
+  w.plans = reinterpret_cast<__nv_bfloat16*>(take((size_t)4 * B * kTok * kLDP * 2));
+  w.eps = reinterpret_cast<float*>(take((size_t)B * kMaxEps * 4));
+  w.n_eps = reinterpret_cast<int*>(take((size_t)B * 4));
+  w.partials = reinterpret_cast<double*>(take((size_t)B * 3 * sizeof(double)));
+  w.bytes = off;
+  return w;
+}
+
+int make_cloud_tmap(CUtensorMap* out, const void* base, int64_t B, int box_rows, const char* what) {
+  const int64_t M = B * kTok;
+  const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)kTok, (uint64_t)B, 2};
+  const uint64_t strides[3] = {(uint64_t)kD * 2, (uint64_t)kTok * kD * 2, (uint64_t)M * kD * 2};
+  const uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+  return make_tmap_bf16(out, base, 4, dims, strides, box, what);
+}
+
+}  // namespace
+}  // namespace dkd
+
+extern "C" {
+
+size_t dkd_wass_sinkhorn_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision) {
+  (void)n_tok;
+  return dkd::carve(nullptr, B, Ds, Dt, precision == DKD_PREC_BF16X3 ? 2 : 1).bytes;
+}
+
+int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const float* bias, int64_t B, int Ts, int s_off, int Tt,
+                             int t_off, int n_tok, int Ds, int Dt, int dtype, int precision, float scale, void* g_s, float* g_W,
+                             float* g_b, float* loss, void* workspace, size_t workspace_bytes, dkd_stream_t stream) {
+  using namespace dkd;
+  int rc = dkd_check_device();
+  if (rc != DKD_OK) return rc;
+  const char* fn = "dkd_wass_sinkhorn_fwdbwd";
+  DKD_REQUIRE(dtype == DKD_F32 || dtype == DKD_BF16, DKD_E_DTYPE, "%s: dtype %d", fn, dtype);
+  DKD_REQUIRE(precision == DKD_PREC_BF16 || precision == DKD_PREC_BF16X3, DKD_E_UNSUPPORTED, "%s: precision %d", fn, precision);
+  DKD_REQUIRE(n_tok == kTok, DKD_E_SHAPE, "%s: built for %d patch tokens per sample, got %d", fn, kTok, n_tok);
+  DKD_REQUIRE(B > 0 && s_off >= 0 && t_off >= 0 && Ts >= s_off + n_tok && Tt >= t_off + n_tok, DKD_E_SHAPE, "%s: bad token geometry", fn);
+  DKD_REQUIRE(Ds == 192 && Dt == kD, DKD_E_SHAPE, "%s: built for widths 192 -> 384, got %d -> %d", fn, Ds, Dt);
+  DKD_REQUIRE(s && t && W && loss && workspace, DKD_E_SHAPE, "%s: null pointer", fn);
+  DKD_REQUIRE((((uintptr_t)workspace) & 1023) == 0, DKD_E_ALIGN, "%s: workspace must be 1024-byte aligned", fn);
+  DKD_REQUIRE(B * 6 < (1ll << 24), DKD_E_SHAPE, "%s: too many samples", fn);
+  const int P = precision == DKD_PREC_BF16X3 ? 2 : 1;
+  const int64_t M = B * kTok;
+  Workspace ws = carve(workspace, B, Ds, Dt, P);
+  DKD_REQUIRE(workspace_bytes >= ws.bytes, DKD_E_WORKSPACE, "%s: workspace %zu < %zu", fn, workspace_bytes, ws.bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool want_grads = g_s || g_W || g_b;
+  const int pairs = (int)B;
+
+  // 1-3. aligned student rows (fp32)
+  rc = launch_tokens_to_planes(s, dtype, B, Ts, s_off, n_tok, Ds, P, nullptr, ws.S, st);
+  if (rc != DKD_OK) return rc;
+  rc = launch_weight_to_planes(W, Dt, Ds, P, ws.Wp, want_grads ? ws.Wt : nullptr, st);
+  if (rc != DKD_OK) return rc;
+  rc = align_forward_rows(ws.S, ws.Wp, bias, ws.A, M, Ds, Dt, P, st, "dkd_wass_sinkhorn_fwdbwd: align GEMM");
+  if (rc != DKD_OK) return rc;
+
+  // 4. point-cloud planes, norms, eps ladders
+  rc = launch_tokens_to_planes(ws.A, DKD_F32, B, kTok, 0, kTok, Dt, 2, nullptr, ws.Xp, st);
+  if (rc != DKD_OK) return rc;
+  rc = launch_tokens_to_planes(t, dtype, B, Tt, t_off, kTok, Dt, 2, nullptr, ws.Yp, st);
+  if (rc != DKD_OK) return rc;
+  PrepParams pp;
+  pp.A = ws.A; pp.t = t; pp.nx = ws.nx; pp.ny = ws.ny; pp.eps = ws.eps; pp.n_eps = ws.n_eps;
+  pp.Tt = Tt; pp.t_off = t_off; pp.t_is_bf16 = dtype == DKD_BF16; pp.blur = 0.05f; pp.scaling = 0.5f;
+  sinkhorn_prep_kernel<<<pairs, kD, 0, st>>>(pp);
+  rc = check_launch("dkd_wass_sinkhorn_fwdbwd: eps ladder");
+  if (rc != DKD_OK) return rc;
+  sinkhorn_norms_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(pp, M);
+  rc = check_launch("dkd_wass_sinkhorn_fwdbwd: norms");
+  if (rc != DKD_OK) return rc;
+
+  {  // 5. cost matrices
+    using Cfg = CostCfg;
+    GemmParams<CostLoader, CostEpi> p;
+    rc = make_cloud_tmap(&p.ld.tmXa, ws.Xp, B, 128, "sinkhorn x (rows)");
+    if (rc != DKD_OK) return rc;
+    rc = make_cloud_tmap(&p.ld.tmXb, ws.Xp, B, 208, "sinkhorn x (cols)");
+    if (rc != DKD_OK) return rc;
+    rc = make_cloud_tmap(&p.ld.tmYa, ws.Yp, B, 128, "sinkhorn y (rows)");
+    if (rc != DKD_OK) return rc;
+    rc = make_cloud_tmap(&p.ld.tmYb, ws.Yp, B, 208, "sinkhorn y (cols)");
+    if (rc != DKD_OK) return rc;
+    p.ld.nterms = 3;
+    p.ep.nx = ws.nx; p.ep.ny = ws.ny; p.ep.C = ws.C;
+    p.m_tiles = pairs * 6; p.n_tiles = 1;
+    const int grid = min(kNumSMs, p.m_tiles);
+    auto kern = gemm_tn_kernel<Cfg, CostLoader, CostEpi>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+    rc = check_launch("dkd_wass_sinkhorn_fwdbwd: cost GEMM");
+    if (rc != DKD_OK) return rc;
+  }
+  {  // 6. Sinkhorn loops
+    SinkParams sp;
+    sp.C = ws.C; sp.eps = ws.eps; sp.n_eps = ws.n_eps; sp.plans = ws.plans; sp.partials = ws.partials;
+    sp.pairs = pairs; sp.write_plans = want_grads;
+    cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSinkSmem);
+    cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSinkSmem);
+    sinkhorn_kernel<true><<<pairs, 2 * kRoleThreads, kSinkSmem, st>>>(sp);
+    rc = check_launch("dkd_wass_sinkhorn_fwdbwd: sinkhorn xy");
+    if (rc != DKD_OK) return rc;
+    sinkhorn_kernel<false><<<pairs * 2, kRoleThreads, kSinkSmem, st>>>(sp);
+    rc = check_launch("dkd_wass_sinkhorn_fwdbwd: sinkhorn xx/yy");
+    if (rc != DKD_OK) return rc;
+    rc = launch_fold_partials(ws.partials, pairs * 3, scale, loss, st);
+    if (rc != DKD_OK) return rc;
+  }
+  if (!want_grads) return DKD_OK;
+
+  {  // 7. g_a planes
+    using Cfg = GradCfg;
+    GemmNtParamsT<Cfg, PlanLoader> p;
+    {
+      const uint64_t dims[4] = {(uint64_t)kTok, (uint64_t)kTok, (uint64_t)B, 4};
+      const uint64_t strides[3] = {(uint64_t)kLDP * 2, (uint64_t)kTok * kLDP * 2, (uint64_t)B * kTok * kLDP * 2};
+      const uint32_t box[4] = {64, 128, 1, 1};
+      rc = make_tmap_bf16(&p.ld.tmPlan, ws.plans, 4, dims, strides, box, "sinkhorn plans");
+      if (rc != DKD_OK) return rc;
+    }
+    rc = make_cloud_tmap(&p.ld.tmX, ws.Xp, B, 64, "sinkhorn x (k rows)");
+    if (rc != DKD_OK) return rc;
+    rc = make_cloud_tmap(&p.ld.tmY, ws.Yp, B, 64, "sinkhorn y (k rows)");
+    if (rc != DKD_OK) return rc;
+    p.ld.pairs = pairs;
+    p.nterms = 3;
+    p.ep.D = nullptr; p.ep.Dcol = nullptr; p.ep.ldd = kD; p.ep.alpha = scale / (float)kTok;
+    p.ep.Dplanes = ws.G; p.ep.plane_stride = M * kD; p.ep.n_planes = 2;
+    const int grid = min(kNumSMs, pairs * 2);
+    auto kern = gemm_nt_kernel<Cfg, PlanLoader>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+    rc = check_launch("dkd_wass_sinkhorn_fwdbwd: plan GEMM");
+    if (rc != DKD_OK) return rc;
+  }
+  // 8-9. through the alignment head (G planes are laid out [2][M][Dt]; a one-pass run reads the hi plane only)
+  if (g_s) {
+    rc = align_dgrad(ws.G, ws.Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, dtype == DKD_BF16, 1.f, st, "dkd_wass_sinkhorn_fwdbwd: dgrad GEMM");
+    if (rc != DKD_OK) return rc;
+  }
+  if (g_W || g_b) {
+    DKD_REQUIRE(g_W != nullptr, DKD_E_UNSUPPORTED, "%s: g_b without g_W is not supported", fn);
+    rc = align_wgrad(ws.G, ws.S, ws.ones, g_W, g_b, M, Ds, Dt, P, 1.f, st, "dkd_wass_sinkhorn_fwdbwd: wgrad GEMM");
+    if (rc != DKD_OK) return rc;
+  }
+  return DKD_OK;
+}
+
+}  // extern "C"

@@ -257,6 +257,15 @@ def wass_l1_loss(s_feats, t_feats, linears, weight: float = 5.0, s_off: int = 1,
     return align_mse_layers_loss(s_feats, t_feats, linears, weight / (n * numel), s_off, t_off, _entry="dkd_wass_l1")
 
 
+def wass_sinkhorn_loss(s_feats, t_feats, linears, weight: float = 5.0, s_off: int = 1, t_off: int = 2):
+    """weight * mean_i [ sum_b Sinkhorn(linears[i](s_i[b, s_off:]), t_i[b, t_off:]) / (B*N) ]  (loss.py:200-226), with
+    Sinkhorn = geomloss.SamplesLoss("sinkhorn", blur=0.05) as restated in oracle/sinkhorn.py."""
+    n = len(linears)
+    B, Ts, _ = s_feats[0].shape
+    return align_mse_layers_loss(s_feats, t_feats, linears, weight / (n * B * (Ts - s_off)), s_off, t_off,
+                                 _entry="dkd_wass_sinkhorn")
+
+
 # --------------------------------------------------------------------------- masked generation (MGD family)
 class _MaskedGeneration(torch.autograd.Function):
     @staticmethod

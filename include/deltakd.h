@@ -142,6 +142,26 @@ DKD_API int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, con
                                dkd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * WassKD 'sinkhorn' term of one layer, forward + backward:
+ *     a = s[:, s_off:, :] W^T + bias ;  per sample b: S_b = debiased Sinkhorn divergence (p = 2, blur = 0.05,
+ *     scaling = 0.5, uniform weights) between the n_tok points a[b] and t[b, t_off:, :] in R^Dt
+ *     *loss += scale * sum_b S_b        (accumulates);   g_a = scale * dS_b/da -> g_s, g_W, g_b   (overwritten)
+ * Replaces the per-sample Python loop over geomloss.SamplesLoss("sinkhorn", blur=0.05) of model/loss.py:200-225
+ * (one host read-back of the diameter and ~60 logsumexp launches per sample there) and its backward; the caller
+ * folds 5/(3*B*n_tok) into `scale`.  geomloss is absent and unpinned in the reference: the arithmetic follows
+ * upstream geomloss 0.2.x (tensorized sinkhorn_loop with symmetric updates, eps ladder from the bounding-box
+ * diameter, last extrapolation step differentiated through the cost matrices only) — oracle/sinkhorn.py.
+ * The eps ladder is built on the device (no synchronisation).  Same argument conventions as
+ * dkd_align_mse_fwdbwd; n_tok must be 196, Ds = 192, Dt = 384.  The cost and plan contractions always run
+ * bf16x3; `precision` applies to the alignment head.
+ */
+DKD_API size_t dkd_wass_sinkhorn_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
+DKD_API int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const float* bias, int64_t B, int Ts,
+                                     int s_off, int Tt, int t_off, int n_tok, int Ds, int Dt, int dtype, int precision,
+                                     float scale, void* g_s, float* g_W, float* g_b, float* loss, void* workspace,
+                                     size_t workspace_bytes, dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Masked generative distillation core, forward + backward (14x14 token grid, Ds = 192, Dt = 384):
  *     x   = s[:, s_off:, :] W_align^T + b_align
  *     x_m = where(mask, mask_token, x)
