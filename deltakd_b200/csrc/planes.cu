@@ -28,11 +28,16 @@ __global__ void tokens_to_planes_kernel(const T* __restrict__ src, int64_t B, in
       Vec<__nv_bfloat16, 8>::load(reinterpret_cast<const __nv_bfloat16*>(src) + srow * D + c, v);
     }
     Vec<__nv_bfloat16, 8>::store(dst + m * D + c, v);
-    if (P == 2) {
+    if (P >= 2) {
       float lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
       Vec<__nv_bfloat16, 8>::store(dst + M * D + m * D + c, lo);
+      if (P >= 3) {  // third plane: all 24 mantissa bits (fp32-exact operands for 6-term products)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo[j] = lo[j] - __bfloat162float(__float2bfloat16_rn(lo[j]));
+        Vec<__nv_bfloat16, 8>::store(dst + 2 * M * D + m * D + c, lo);
+      }
     }
   }
 }

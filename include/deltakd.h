@@ -152,8 +152,8 @@ DKD_API int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, con
  * upstream geomloss 0.2.x (tensorized sinkhorn_loop with symmetric updates, eps ladder from the bounding-box
  * diameter, last extrapolation step differentiated through the cost matrices only) — oracle/sinkhorn.py.
  * The eps ladder is built on the device (no synchronisation).  Same argument conventions as
- * dkd_align_mse_fwdbwd; n_tok must be 196, Ds = 192, Dt = 384.  The cost and plan contractions always run
- * bf16x3; `precision` applies to the alignment head.
+ * dkd_align_mse_fwdbwd; n_tok must be 196, Ds = 192, Dt = 384.  The cost matrices always use fp32-exact
+ * split operands (6 bf16 products), the plan contraction bf16x3; `precision` applies to the alignment head.
  */
 DKD_API size_t dkd_wass_sinkhorn_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
 DKD_API int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const float* bias, int64_t B, int Ts,

@@ -2,9 +2,11 @@
 GEMMs) vs the oracle restatement of geomloss (PARITY UNPINNED: geomloss is absent from the reference tree, see
 oracle/sinkhorn.py) and the goldens the reference's own loss.py produced through that restatement.
 
-At blur = 0.05 (eps = 0.0025) the transport plans are nearly one-hot: the gradient is an assignment and is
-discontinuous where two candidate partners tie.  The gradient gate is therefore 1e-4 relative plus the worth of
-the rows whose best and second-best partners are within the fp32 resolution of the cost (reported, capped)."""
+At blur = 0.05 (eps = 0.0025) the softmin arguments are ~4e4 in magnitude, so ANY fp32 evaluation resolves them
+to ~4e-3: the ~17 % of plan rows that are not one-hot carry that noise into the gradient.  The reference's own
+fp32 arithmetic (the oracle run in float32) is ~1.5e-4 away from the float64 result on these inputs.  The
+gradient gate is therefore  1e-4 + 2 x (that measured fp32-vs-fp64 distance of the reference arithmetic),
+computed in the test; the loss gate stays 1e-5."""
 import pytest
 import torch
 
@@ -35,13 +37,22 @@ def test_wass_sinkhorn_matches_reference(golden):
     ol = O.distillation_loss(o.kind, o.outputs, o.labels, o.teacher_logits, o.s_feats, o.t_feats, oh, o.args, o.alpha, o.tau)
     ol.backward()
     assert abs(loss.item() - ol.item()) <= LOSS_RTOL * abs(ol.item()), (loss.item(), ol.item())
+    # the reference arithmetic in its own precision (float32), for the noise floor of the gradient gate
+    r = build_case(name, dtype=torch.float32)
+    rh = H.head_tensors(r.student)
+    O.distillation_loss(r.kind, r.outputs, r.labels, r.teacher_logits, r.s_feats, r.t_feats, rh, r.args, r.alpha, r.tau).backward()
     for i in range(3):
-        assert rel_err(c.s_feats[i].grad, o.s_feats[i].grad) < GRAD_RTOL, f"g_sfeat{i}"
+        floor = rel_err(r.s_feats[i].grad, o.s_feats[i].grad)
+        assert floor < 1e-3
+        err = rel_err(c.s_feats[i].grad, o.s_feats[i].grad)
+        assert err < GRAD_RTOL + 2 * floor, f"g_sfeat{i}: {err} (fp32 reference arithmetic: {floor})"
         assert float(c.s_feats[i].grad[:, 0].abs().max()) == 0.0
         assert rel_err(digest(c.s_feats[i].grad), golden[f"{name}/f64/g_sfeat{i}"]) < GRAD_RTOL
         for part in ("weight", "bias"):
             k = f"align_wasskd.{i}.{part}"
-            assert rel_err(heads[k].grad, oh[k].grad) < GRAD_RTOL, k
+            floor = rel_err(rh[k].grad, oh[k].grad)
+            err = rel_err(heads[k].grad, oh[k].grad)
+            assert err < GRAD_RTOL + 2 * floor, f"{k}: {err} (fp32 reference arithmetic: {floor})"
     for i in range(3, 12):
         assert c.s_feats[i].grad is None
 
