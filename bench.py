@@ -184,6 +184,15 @@ class LogitKD(Workload):
         return l
 
 
+class LogitKDLargeBatch(LogitKD):
+    """The same fused logit kernel at B = 16 384 (197 MB of algorithmic traffic): configs[1] itself moves 3 MB and is
+    launch-bound by construction, so the kernel's bandwidth fraction is shown on this batch sweep point."""
+    name = "soft_kd_logits_b16384_c1000_bf16"
+    B = 16384
+    cpu_B = 2048
+    default_steps = 20
+
+
 class FeatureKD(Workload):
     """Feature-level losses: student block outputs [B,197,192], teacher [B,198,384], heads on the student."""
     kind = ""
@@ -409,7 +418,7 @@ class MGDBf16(MGD):
 
 
 HEADLINE = LogitKD
-EXTRAS = (CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16, SaliencyMGD, LRKD, WassL1, WassSinkhorn)
+EXTRAS = (LogitKDLargeBatch, CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16, SaliencyMGD, LRKD, WassL1, WassSinkhorn)
 WORKLOADS = {w.name: w for w in (HEADLINE,) + EXTRAS}
 
 

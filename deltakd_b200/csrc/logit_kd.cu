@@ -33,7 +33,7 @@ struct LogitKdParams {
 // NV > 0: row cached in registers (C <= kThreads*VEC*NV).  NV == 0: streaming (re-read) path.
 template <typename T, int VEC, int NV>
 __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
-  __shared__ float scratch[4 * (kThreads / 32)];
+  __shared__ float scratch[8 * (kThreads / 32)];
   __shared__ int s_arg[kThreads / 32];
   __shared__ float s_argv[kThreads / 32];
   __shared__ bool s_last;
@@ -128,24 +128,33 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
   // ---- pass 2: sums --------------------------------------------------------------------------
   // s[0]=sum exp(z-m0)  s[1]=sum exp(a-m1)  s[2]=sum exp(b-m2)  s[3]=sum exp(b-m2)*(b-a)
   // t[0]=sum y          t[1]=sum y*z (soft labels) | sum z (int labels)   t[2]=z[label]  t[3]=zk[hard_idx]
-  float s[4] = {0.f, 0.f, 0.f, 0.f}, t[4] = {0.f, 0.f, 0.f, 0.f};
+  // In the register-resident case the exponentials replace the logits in rz / rk / rt (pass 3 needs only them,
+  // the soft labels and the column index), so every exp is evaluated once.
+  float st8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float (&s)[4] = *reinterpret_cast<float(*)[4]>(&st8[0]);
+  float (&t)[4] = *reinterpret_cast<float(*)[4]>(&st8[4]);
   auto pass2 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
     const int64_t col = col_of(it);
     if (col < C) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        s[0] += expf(a[v] - mx[0]);
+        const float ea = expf(a[v] - mx[0]);
+        s[0] += ea;
         if (p.label_kind == 0) { t[0] += d[v]; t[1] += d[v] * a[v]; }
         else { t[1] += a[v]; if (col + v == label) t[2] = a[v]; }
+        if (NV > 0) a[v] = ea;
         if (p.kd_kind == 1) {
           const float av = b[v] * invT, bv = c[v] * invT;
-          const float eb = expf(bv - mx[2]);
-          s[1] += expf(av - mx[1]);
+          const float eb = expf(bv - mx[2]), es = expf(av - mx[1]);
+          s[1] += es;
           s[2] += eb;
           s[3] += eb * (bv - av);
+          if (NV > 0) { b[v] = es; c[v] = eb; }
         } else if (p.kd_kind == 2) {
-          s[1] += expf(b[v] - mx[1]);
+          const float es = expf(b[v] - mx[1]);
+          s[1] += es;
           if (col + v == hard_idx) t[3] = b[v];
+          if (NV > 0) b[v] = es;
         }
       }
     }
@@ -159,8 +168,7 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
       pass2(it, rz[0], rk[0], rt[0], ry[0]);
     }
   }
-  block_sum<4, kThreads>(s, scratch);
-  block_sum<4, kThreads>(t, scratch);
+  block_sum<8, kThreads>(st8, scratch);
 
   const float Bf = (float)p.B, Cf = (float)C;
   const float lse0 = mx[0] + logf(s[0]);
@@ -190,15 +198,15 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
       float g0[VEC], g1[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float sm = expf(a[v] - mx[0]) * inv_s0;
+        const float sm = (NV > 0 ? a[v] : expf(a[v] - mx[0])) * inv_s0;
         if (p.label_kind == 0) g0[v] = (sm * t[0] - d[v]) * wb;
         else g0[v] = (sm - (col + v == label ? 1.f - p.smoothing : 0.f) - p.smoothing / Cf) * wb;
         if (p.kd_kind == 1) {
-          const float ps = expf(b[v] * invT - mx[1]) * inv_s1;
-          const float pt = expf(c[v] * invT - mx[2]) * inv_s2;
+          const float ps = (NV > 0 ? b[v] : expf(b[v] * invT - mx[1])) * inv_s1;
+          const float pt = (NV > 0 ? c[v] : expf(c[v] * invT - mx[2])) * inv_s2;
           g1[v] = (ps - pt) * wk;
         } else if (p.kd_kind == 2) {
-          const float ps = expf(b[v] - mx[1]) * inv_s1;
+          const float ps = (NV > 0 ? b[v] : expf(b[v] - mx[1])) * inv_s1;
           g1[v] = (ps - (col + v == hard_idx ? 1.f : 0.f)) * wk;
         }
       }

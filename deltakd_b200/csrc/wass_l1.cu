@@ -7,10 +7,11 @@
 //   1-2. operand planes (S, W) as in align_mse.cu
 //   3.   a = S W^T + b  (gemm_tn, fp32 rows to scratch)
 //   4.   sort kernel: one CTA per (sample, 32-channel group); the [n_tok x 32] student and teacher tiles are
-//        staged in shared memory with coalesced 128-byte rows; each warp sorts whole columns with a 256-wide
-//        bitonic network held in registers (8 keys per lane, cross-lane steps by warp shuffle; the student
-//        carries its token index as payload, ties ordered by index); |diff| is block-reduced and sign(diff)
-//        is scattered back through shared memory so the +-1 gradient plane is written with full rows.
+//        staged (transposed) in shared memory from coalesced 128-byte rows; 4 adjacent lanes sort one column with
+//        a 256-wide keys-only bitonic network held in registers (64 keys per lane: 33 of the 36 stages are
+//        in-register FMNMX pairs, 3 use warp shuffles); the permutation is recovered by a binary search of each
+//        student value in its sorted column (duplicates ordered by token index); |diff| is block-reduced and
+//        sign(diff) goes back through shared memory so the +-1 gradient plane is written with full rows.
 //   5-6. g_s = c * G W, g_W = c * G^T S, g_b = c * G^T 1  (tcgen05; c = scale folded into the epilogues)
 // The sort is on-chip (shared memory + registers): HBM traffic is the a/t tile reads and the +-1 plane write.
 #include "epilogues.cuh"
@@ -20,51 +21,51 @@
 namespace dkd {
 namespace {
 
-constexpr int kSortThreads = 256;
-constexpr int kCh = 32;        // channels per CTA
-constexpr int kMaxTok = 256;   // bitonic width
+constexpr int kSortThreads = 128;   // 4 warps x 4 columns x 8 lanes
+constexpr int kCh = 16;             // channels (columns) per CTA
+constexpr int kMaxTok = 256;        // bitonic width
+constexpr int kPerLane = 32;        // keys per lane: a column is held by 8 adjacent lanes
+constexpr int kQuad = kMaxTok / kPerLane;   // 8 lanes per column
 
-struct KV { float v; int i; };
-__device__ __forceinline__ bool kv_less(const KV& a, const KV& b) { return a.v < b.v || (a.v == b.v && a.i < b.i); }
-
-// 256 (key, index) pairs per warp: element e = r*32 + lane lives in slot r of lane.  Ascending on exit.
-template <bool WITH_INDEX>
-__device__ __forceinline__ void warp_bitonic_256(float (&key)[8], int (&idx)[8], int lane) {
+// Keys-only bitonic sort of 256 floats held by 8 adjacent lanes (sorted position e = sub*32 + r, sub = lane & 7).
+// Strides below 32 are in-register compare-exchanges (two FMNMX, 30 stages); strides 32/64/128 (6 stages) cross
+// lanes by shuffle.  Descending sub-sequences (phases k = 32, 64, 128 on the lanes whose position has bit k set) are run
+// as ascending ones on negated keys, so every compare-exchange has a compile-time direction.  Ascending on exit;
+// ties need no order (equal keys are interchangeable in the sorted sequence).
+__device__ __forceinline__ void bitonic256_oct(float (&key)[kPerLane], int sub) {
 #pragma unroll
   for (int k = 2; k <= 256; k <<= 1) {
+    const bool flip = k >= kPerLane && k < 256 && ((sub * kPerLane) & k) != 0;
+    if (k >= kPerLane && k < 256) {
+#pragma unroll
+      for (int r = 0; r < kPerLane; ++r) key[r] = flip ? -key[r] : key[r];
+    }
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const int jr = j >> 5;
+      if (j >= kPerLane) {
+        const int lx = j / kPerLane;                        // partner lane = lane ^ lx
+        const bool keep_min = (sub & lx) == 0;              // lower position of the pair keeps the minimum
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int pr = r ^ jr;
-          if (pr > r) {
-            const int e = r * 32 + lane;
-            const bool up = (e & k) == 0;
-            KV a{key[r], idx[r]}, b{key[pr], idx[pr]};
-            const bool swap = up ? kv_less(b, a) : kv_less(a, b);
-            if (swap) {
-              key[r] = b.v; key[pr] = a.v;
-              if (WITH_INDEX) { idx[r] = b.i; idx[pr] = a.i; }
-            }
-          }
+        for (int r = 0; r < kPerLane; ++r) {
+          const float o = __shfl_xor_sync(0xffffffffu, key[r], lx);
+          key[r] = keep_min ? fminf(key[r], o) : fmaxf(key[r], o);
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int e = r * 32 + lane;
-          const bool up = (e & k) == 0;
-          const bool lower = (lane & j) == 0;       // this lane holds the lower-index element of the pair
-          KV mine{key[r], idx[r]}, other;
-          other.v = __shfl_xor_sync(0xffffffffu, key[r], j);
-          other.i = WITH_INDEX ? __shfl_xor_sync(0xffffffffu, idx[r], j) : 0;
-          if (!WITH_INDEX) { mine.i = lower ? 0 : 1; other.i = lower ? 1 : 0; }  // stable tie-break by position
-          const bool keep_min = (lower == up);
-          const bool take_other = keep_min ? kv_less(other, mine) : kv_less(mine, other);
-          if (take_other) { key[r] = other.v; if (WITH_INDEX) idx[r] = other.i; }
+        for (int r = 0; r < kPerLane; ++r) {
+          if ((r & j) == 0) {
+            const int pr = r | j;
+            const bool up = k >= kPerLane || (r & k) == 0;     // compile-time
+            const float a = key[r], b = key[pr];
+            key[r] = up ? fminf(a, b) : fmaxf(a, b);
+            key[pr] = up ? fmaxf(a, b) : fminf(a, b);
+          }
         }
       }
+    }
+    if (k >= kPerLane && k < 256) {
+#pragma unroll
+      for (int r = 0; r < kPerLane; ++r) key[r] = flip ? -key[r] : key[r];
     }
   }
 }
@@ -75,51 +76,133 @@ struct SortParams {
   __nv_bfloat16* G;      // [P][M][N] : plane 0 = sign(diff) in {-1,0,+1}, plane 1 (if any) = 0
   double* partials;      // [gridDim]
   int64_t M;
-  int N, n_tok, Tt, t_off, planes, t_is_bf16, write_grad;
+  int N, n_tok, Tt, t_off, planes, t_is_bf16, write_grad, pitch;
 };
 
+// One CTA per (sample, 16-channel group).  Shared memory holds three transposed tiles [16 columns][pitch]:
+//   sa  : student values (later: the +-1 gradient, in place)      st : teacher values -> sorted teacher (in place)
+//   ssa : sorted student
+// A warp owns 4 columns (8 lanes each).  Both sequences are sorted keys-only; the permutation is never carried:
+// the rank of a student value is its lower bound in the sorted student column (duplicates are ordered by token
+// index, as the oracle's stable sort does), and d|.|/da = sign(a - sorted_t[rank]).
 __global__ void __launch_bounds__(kSortThreads) wass_sort_kernel(SortParams p) {
-  extern __shared__ float smem_f[];
-  float (*sa)[kCh + 1] = reinterpret_cast<float (*)[kCh + 1]>(smem_f);                          // [n_tok][33]
-  float (*st)[kCh + 1] = reinterpret_cast<float (*)[kCh + 1]>(smem_f + (size_t)p.n_tok * (kCh + 1));
+  extern __shared__ __align__(16) float smem_f[];
+  const int pitch = p.pitch;     // 264
+  float* sa = smem_f;
+  float* st = sa + kCh * pitch;
+  float* ssa = st + kCh * pitch;
   __shared__ float red[kSortThreads / 32];
   const int groups = p.N / kCh;
   const int b = blockIdx.x / groups, c0 = (blockIdx.x % groups) * kCh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_tok = p.n_tok;
 
-  // coalesced tile loads: 32 consecutive channels (128 B) per token row
-  for (int tok = warp; tok < p.n_tok; tok += kSortThreads / 32) {
-    const int64_t toff = ((int64_t)b * p.Tt + p.t_off + tok) * p.N + c0 + lane;
-    sa[tok][lane] = p.a[((int64_t)b * p.n_tok + tok) * p.N + c0 + lane];
-    st[tok][lane] = p.t_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.t)[toff]) : reinterpret_cast<const float*>(p.t)[toff];
-  }
-  __syncthreads();
-
-  float local = 0.f;
-  for (int col = warp; col < kCh; col += kSortThreads / 32) {
-    float ka[8], kt[8];
-    int ia[8], it_[8];
+  // tile loads: a thread owns one 16-byte chunk (4 channels) of every 32nd token; all loads are issued before the
+  // first transposing store (the fill is otherwise a chain of DRAM round trips)
+  {
+    constexpr int kSlots = kMaxTok / (kSortThreads / 4);   // 8 token slots per thread
+    const int ch = (threadIdx.x & 3) * 4, tok0 = threadIdx.x >> 2;
+    float4 va[kSlots], vt[kSlots];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int e = r * 32 + lane;
-      const bool real = e < p.n_tok;          // slots beyond n_tok are +inf padding that sorts to the end
-      ka[r] = real ? sa[e][col] : INFINITY; ia[r] = e;
-      kt[r] = real ? st[e][col] : INFINITY; it_[r] = 0;
+    for (int k = 0; k < kSlots; ++k) {
+      const int tok = tok0 + k * (kSortThreads / 4);
+      if (tok < n_tok) {
+        va[k] = __ldg(reinterpret_cast<const float4*>(p.a + ((int64_t)b * n_tok + tok) * p.N + c0 + ch));
+        const int64_t toff = ((int64_t)b * p.Tt + p.t_off + tok) * p.N + c0 + ch;
+        if (p.t_is_bf16) {
+          float v[4];
+          Vec<__nv_bfloat16, 4>::load(reinterpret_cast<const __nv_bfloat16*>(p.t) + toff, v);
+          vt[k] = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          vt[k] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.t) + toff));
+        }
+      }
     }
-    warp_bitonic_256<true>(ka, ia, lane);
-    warp_bitonic_256<false>(kt, it_, lane);
-    __syncwarp();
+    float* da = sa + ch * pitch + tok0;
+    float* dt = st + ch * pitch + tok0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int e = r * 32 + lane;
-      if (e < p.n_tok) {
-        const float d = ka[r] - kt[r];
-        local += fabsf(d);
-        // gradient of |d| w.r.t. the student element that landed at sorted position e
-        sa[ia[r]][col] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    for (int k = 0; k < kSlots; ++k) {
+      const int o = k * (kSortThreads / 4);
+      if (tok0 + o < n_tok) {
+        da[o] = va[k].x; da[pitch + o] = va[k].y; da[2 * pitch + o] = va[k].z; da[3 * pitch + o] = va[k].w;
+        dt[o] = vt[k].x; dt[pitch + o] = vt[k].y; dt[2 * pitch + o] = vt[k].z; dt[3 * pitch + o] = vt[k].w;
       }
     }
   }
+  __syncthreads();
+
+  const int sub = lane & (kQuad - 1);
+  const int col = warp * 4 + (lane >> 3);
+  float* ca = sa + col * pitch;
+  float* ct = st + col * pitch;
+  float* cs = ssa + col * pitch;
+  float key[kPerLane];
+  float local = 0.f;
+
+  // pass 0: teacher column, pass 1: student column — gather (token q*8 + sub: conflict-free), sort, store sorted
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* src = pass ? ca : ct;
+    float* dst = pass ? cs : ct;
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q) { const int tok = q * kQuad + sub; key[q] = tok < n_tok ? src[tok] : INFINITY; }
+    __syncwarp();
+    bitonic256_oct(key, sub);
+#pragma unroll
+    for (int r = 0; r < kPerLane; r += 4)
+      if (sub * kPerLane + r < pitch) *reinterpret_cast<float4*>(dst + sub * kPerLane + r) = make_float4(key[r], key[r + 1], key[r + 2], key[r + 3]);
+  }
+#pragma unroll
+  for (int r = 0; r < kPerLane; r += 4) {   // key[] still holds the sorted student column
+    const int e = sub * kPerLane + r;
+    if (e < n_tok) {                          // n_tok % 4 == 0 is not required: +inf - +inf never enters (guards below)
+      const float4 tv = *reinterpret_cast<const float4*>(ct + e);
+      if (e + 0 < n_tok) local += fabsf(key[r + 0] - tv.x);
+      if (e + 1 < n_tok) local += fabsf(key[r + 1] - tv.y);
+      if (e + 2 < n_tok) local += fabsf(key[r + 2] - tv.z);
+      if (e + 3 < n_tok) local += fabsf(key[r + 3] - tv.w);
+    }
+  }
+  __syncwarp();
+
+  if (p.write_grad) {
+    // sign of (student value - its teacher partner), two bit masks per lane (token q*8 + sub -> bit q);
+    // 4 independent searches in flight
+    unsigned pos = 0u, neg = 0u;
+#pragma unroll 1
+    for (int q0 = 0; q0 * kQuad + sub < n_tok; q0 += 4) {
+      float v[4];
+      int r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tok = (q0 + u) * kQuad + sub;
+        v[u] = tok < n_tok ? ca[tok] : INFINITY;
+        r[u] = 0;
+      }
+#pragma unroll
+      for (int step = 128; step > 0; step >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] += cs[r[u] + step - 1] < v[u] ? step : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tok = (q0 + u) * kQuad + sub;
+        if (tok < n_tok) {
+          int rk = r[u];
+          if (cs[rk + 1] == v[u])                          // duplicates: earlier tokens first
+            for (int j = 0; j < tok; ++j) rk += (ca[j] == v[u]) ? 1 : 0;
+          const float d = v[u] - ct[rk];
+          pos |= (unsigned)(d > 0.f) << (q0 + u);
+          neg |= (unsigned)(d < 0.f) << (q0 + u);
+        }
+      }
+    }
+    __syncwarp();   // every lane of the column is done reading the student values
+#pragma unroll 4
+    for (int q = 0; q < kPerLane; ++q)
+      if (q * kQuad + sub < n_tok) ca[q * kQuad + sub] = ((pos >> q) & 1u) ? 1.f : (((neg >> q) & 1u) ? -1.f : 0.f);
+  }
+
   local = warp_sum(local);
   if (lane == 0) red[warp] = local;
   __syncthreads();
@@ -129,11 +212,20 @@ __global__ void __launch_bounds__(kSortThreads) wass_sort_kernel(SortParams p) {
     p.partials[blockIdx.x] = s;
   }
   if (!p.write_grad) return;
-  // +-1 gradient plane, 64-byte rows per CTA (32 bf16 channels)
-  for (int tok = warp; tok < p.n_tok; tok += kSortThreads / 32) {
-    const int64_t off = ((int64_t)b * p.n_tok + tok) * p.N + c0 + lane;
-    p.G[off] = __float2bfloat16_rn(sa[tok][lane]);
-    if (p.planes == 2) p.G[p.M * p.N + off] = __float2bfloat16_rn(0.f);
+  // +-1 gradient plane: a thread converts 4 channels of a token (8-byte stores, 32-byte rows per CTA)
+  {
+    const int ch = (threadIdx.x & 3) * 4;
+    for (int tok = threadIdx.x >> 2; tok < n_tok; tok += kSortThreads / 4) {
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = sa[(ch + q) * pitch + tok];
+      const int64_t off = ((int64_t)b * n_tok + tok) * p.N + c0 + ch;
+      Vec<__nv_bfloat16, 4>::store(p.G + off, v);
+      if (p.planes == 2) {
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        Vec<__nv_bfloat16, 4>::store(p.G + p.M * p.N + off, z);
+      }
+    }
   }
 }
 
@@ -226,7 +318,8 @@ int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float
     SortParams sp;
     sp.a = ws.A; sp.t = t; sp.G = ws.G; sp.partials = ws.partials; sp.M = M; sp.N = Dt; sp.n_tok = n_tok; sp.Tt = Tt;
     sp.t_off = t_off; sp.planes = P; sp.t_is_bf16 = dtype == DKD_BF16; sp.write_grad = want_grads;
-    const size_t sort_smem = (size_t)2 * n_tok * (kCh + 1) * sizeof(float);
+    sp.pitch = kMaxTok + 8;   // all 256 sorted slots (+inf padded) are stored; 264 = 8 mod 32: a warp's 4 columns gather from 32 banks
+    const size_t sort_smem = (size_t)3 * kCh * sp.pitch * sizeof(float);
     cudaFuncSetAttribute(wass_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
     wass_sort_kernel<<<sort_grid, kSortThreads, sort_smem, st>>>(sp);
     rc = check_launch("dkd_wass_l1_fwdbwd: sort");
