@@ -1,6 +1,7 @@
 // The three tcgen05 GEMMs around a Linear(Ds -> Dt) alignment head, shared by the losses that need the aligned
 // activations themselves (WassKD): forward rows, and the backward from a gradient-plane tensor G[P][M][Dt].
-//   align_forward_rows : A[M, Dt] fp32 = S W^T + bias                 (gemm_tn, StoreRows epilogue)
+//   align_forward_rows     : A[M, Dt] fp32 = S W^T + bias                 (gemm_tn, StoreRows epilogue)
+//   align_forward_residual : G = gscale (S W^T + bias - t), loss partials   (gemm_tn, ResidualMse epilogue)
 //   align_dgrad        : g_s[:, off:, :] = alpha * G W                (gemm_tn, rows scattered, special tokens zeroed)
 //   align_wgrad        : g_W = alpha * G^T S, g_b = alpha * G^T 1     (gemm_nt split-K, ones-column trick)
 #pragma once
@@ -32,6 +33,32 @@ inline int align_forward_rows(const __nv_bfloat16* S, const __nv_bfloat16* Wp, c
   auto kern = gemm_tn_kernel<Cfg, L, E>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+  return check_launch(what);
+}
+
+// d = S W^T + bias - t[:, t_off:] ; per-CTA loss partials ; G = gscale * d as planes (teacher read in place).
+// `grid_out` = number of partials written.
+inline int align_forward_residual(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, const void* t, int t_is_bf16,
+                                  int Tt, int t_off, int n_tok, __nv_bfloat16* G, double* partials, float gscale, int64_t M, int Ds,
+                                  int Dt, int P, cudaStream_t st, int* grid_out, const char* what) {
+  using Cfg = AlignFwdCfg;
+  using L = PlaneLoader<Cfg>;
+  using E = ResidualMseEpi<Cfg>;
+  GemmParams<L, E> p;
+  int rc = make_plane_tmap(&p.ld.tmA, S, P, M, Ds, Ds, M * Ds, Cfg::BM, what);
+  if (rc != DKD_OK) return rc;
+  rc = make_plane_tmap(&p.ld.tmB, Wp, P, Dt, Ds, Ds, (int64_t)Dt * Ds, Cfg::BN, what);
+  if (rc != DKD_OK) return rc;
+  p.ld.k_blocks = Ds / 64; p.ld.nterms = P == 2 ? 3 : 1;
+  p.ep.t = t; p.ep.bias = bias; p.ep.G = G; p.ep.partials = partials;
+  p.ep.M = M; p.ep.N = Dt; p.ep.n_tok = n_tok; p.ep.Tt = Tt; p.ep.t_off = t_off; p.ep.planes = P;
+  p.ep.gscale = gscale; p.ep.t_is_bf16 = t_is_bf16;
+  p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM); p.n_tiles = Dt / Cfg::BN;
+  const int grid = min(kNumSMs, p.m_tiles * p.n_tiles);
+  auto kern = gemm_tn_kernel<Cfg, L, E>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+  *grid_out = grid;
   return check_launch(what);
 }
 

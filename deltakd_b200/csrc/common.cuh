@@ -106,16 +106,46 @@ template <typename T, int VEC> struct Vec {
   }
 };
 
+// ---- 256-bit global accesses (sm_100: LDG/STG.E.256).  A thread that owns a contiguous run of a row moves it in
+// 32-byte pieces: half the instructions and L1 wavefronts of 16-byte accesses, and every store fills a whole sector.
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+// 16 bf16 <-> 16 fp32
+__device__ __forceinline__ void ldg256(const __nv_bfloat16* p, float (&v)[16]) {
+  uint32_t w[8];
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void stg256(__nv_bfloat16* p, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // fp32 x[32] -> bf16 hi (and lo = x - hi) planes, 64 contiguous bytes each
 __device__ __forceinline__ void store_planes32(__nv_bfloat16* hi_ptr, int64_t plane_stride, int planes, float (&x)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
+  stg256(hi_ptr, *reinterpret_cast<float(*)[16]>(&x[0]));
+  stg256(hi_ptr + 16, *reinterpret_cast<float(*)[16]>(&x[16]));
   if (planes == 2) {
     float lo[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) lo[j] = x[j] - __bfloat162float(__float2bfloat16_rn(x[j]));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(hi_ptr + plane_stride + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
+    stg256(hi_ptr + plane_stride, *reinterpret_cast<float(*)[16]>(&lo[0]));
+    stg256(hi_ptr + plane_stride + 16, *reinterpret_cast<float(*)[16]>(&lo[16]));
   }
 }
 

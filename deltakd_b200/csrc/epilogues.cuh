@@ -46,50 +46,62 @@ struct ResidualMseEpi {
   struct State { float acc; };
   static __device__ __forceinline__ void init(const Params&, State& st) { st.acc = 0.f; }
 
+  // teacher values of one 32-column chunk of this thread's row (zeros when there is no teacher / the row is dead)
+  static __device__ __forceinline__ void load_teacher(const Params& p, bool live, int64_t trow, int col, float (&tv)[32]) {
+    if (p.t == nullptr || !live) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tv[j] = 0.f;
+    } else if (p.t_is_bf16) {
+      const __nv_bfloat16* tp = reinterpret_cast<const __nv_bfloat16*>(p.t) + trow * p.N + col;
+      ldg256(tp, *reinterpret_cast<float(*)[16]>(&tv[0]));
+      ldg256(tp + 16, *reinterpret_cast<float(*)[16]>(&tv[16]));
+    } else {
+      const float* tp = reinterpret_cast<const float*>(p.t) + trow * p.N + col;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ldg256(tp + 8 * j, *reinterpret_cast<float(*)[8]>(&tv[8 * j]));
+    }
+  }
+  static __device__ __forceinline__ void chunk(const Params& p, State& st, bool live, int64_t m, int col, uint32_t t_addr, const float (&tv)[32]) {
+    float v[32];
+    sm100::tmem_ld32(t_addr, v);
+    sm100::tmem_ld_wait();
+    if (live) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[j] + (p.bias ? __ldg(p.bias + col + j) : 0.f) - tv[j];
+        st.acc = fmaf(d, d, st.acc);
+        const float g = p.gscale * d;
+        hi[j] = g;
+        lo[j] = g - __bfloat162float(__float2bfloat16_rn(g));
+      }
+      __nv_bfloat16* gp = p.G + m * p.N + col;
+      stg256(gp, *reinterpret_cast<float(*)[16]>(&hi[0]));
+      stg256(gp + 16, *reinterpret_cast<float(*)[16]>(&hi[16]));
+      if (p.planes == 2) {
+        __nv_bfloat16* gl = gp + p.M * p.N;
+        stg256(gl, *reinterpret_cast<float(*)[16]>(&lo[0]));
+        stg256(gl + 16, *reinterpret_cast<float(*)[16]>(&lo[16]));
+      }
+    }
+  }
+
+  // The teacher chunk of step c+1 is requested before chunk c is processed (two register buffers): each DRAM round
+  // trip overlaps a chunk of TMEM reads, arithmetic and stores instead of being exposed six times per tile.
   static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc) {
+    static_assert((Cfg::BN / 32) % 2 == 0, "chunks are processed in pairs");
     const int64_t m = (int64_t)m0 + row_in_tile;
     const bool live = m < p.M;
     const int64_t b = live ? m / p.n_tok : 0;
     const int64_t trow = b * p.Tt + p.t_off + (live ? m - b * p.n_tok : 0);
+    float ta[32], tb[32];
+    load_teacher(p, live, trow, n0, ta);
 #pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
-      float v[32];
-      sm100::tmem_ld32(t_acc + c0, v);
-      float tv[32];
-      if (p.t == nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tv[j] = 0.f;
-      } else if (live) {
-        if (p.t_is_bf16) {
-          const __nv_bfloat16* tp = reinterpret_cast<const __nv_bfloat16*>(p.t) + trow * p.N + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::load(tp + 8 * j, *reinterpret_cast<float(*)[8]>(&tv[8 * j]));
-        } else {
-          const float* tp = reinterpret_cast<const float*>(p.t) + trow * p.N + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) Vec<float, 4>::load(tp + 4 * j, *reinterpret_cast<float(*)[4]>(&tv[4 * j]));
-        }
-      }
-      sm100::tmem_ld_wait();
-      if (live) {
-        float hi[32], lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = v[j] + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f) - tv[j];
-          st.acc = fmaf(d, d, st.acc);
-          const float g = p.gscale * d;
-          hi[j] = g;
-          lo[j] = g - __bfloat162float(__float2bfloat16_rn(g));
-        }
-        __nv_bfloat16* gp = p.G + m * p.N + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(gp + 8 * j, *reinterpret_cast<float(*)[8]>(&hi[8 * j]));
-        if (p.planes == 2) {
-          __nv_bfloat16* gl = gp + p.M * p.N;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(gl + 8 * j, *reinterpret_cast<float(*)[8]>(&lo[8 * j]));
-        }
-      }
+    for (int c0 = 0; c0 < Cfg::BN; c0 += 64) {
+      load_teacher(p, live, trow, n0 + c0 + 32, tb);
+      chunk(p, st, live, m, n0 + c0, t_acc + c0, ta);
+      if (c0 + 64 < Cfg::BN) load_teacher(p, live, trow, n0 + c0 + 64, ta);
+      chunk(p, st, live, m, n0 + c0 + 32, t_acc + c0 + 32, tb);
     }
   }
 
@@ -142,8 +154,8 @@ struct StoreRowsEpi {
       for (int j = 0; j < 32; ++j) z[j] = 0.f;
       if (p.out_is_bf16) {
         __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.N_total + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(op + 8 * j, *reinterpret_cast<float(*)[8]>(&v[8 * j]));
+        stg256(op, *reinterpret_cast<float(*)[16]>(&v[0]));
+        stg256(op + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
         if (i == 0)  // the special-token rows in front of this sample's patches get zero gradient
           for (int r = 1; r <= p.off; ++r)
 #pragma unroll
@@ -151,7 +163,7 @@ struct StoreRowsEpi {
       } else {
         float* op = reinterpret_cast<float*>(p.out) + orow * p.N_total + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Vec<float, 4>::store(op + 4 * j, *reinterpret_cast<float(*)[4]>(&v[4 * j]));
+        for (int j = 0; j < 4; ++j) stg256(op + 8 * j, *reinterpret_cast<float(*)[8]>(&v[8 * j]));
         if (i == 0)
           for (int r = 1; r <= p.off; ++r)
 #pragma unroll

@@ -140,6 +140,7 @@ int dkd_masked_generation_fwdbwd(const void* s, const void* t, const float* mask
   DKD_REQUIRE(s && t && mask && W_align && mask_token && conv1_w && conv1_b && conv2_w && conv2_b && loss && workspace, DKD_E_SHAPE,
               "%s: null pointer", fn);
   DKD_REQUIRE((((uintptr_t)workspace) & 1023) == 0, DKD_E_ALIGN, "%s: workspace must be 1024-byte aligned", fn);
+  DKD_REQUIRE((((uintptr_t)g_s) & 31) == 0, DKD_E_ALIGN, "%s: g_s must be 32-byte aligned (256-bit stores)", fn);
   const int P = precision == DKD_PREC_BF16X3 ? 2 : 1;
   const int64_t M = B * n_tok;
   DKD_REQUIRE(M < (1ll << 31) - 256, DKD_E_SHAPE, "%s: too many rows", fn);

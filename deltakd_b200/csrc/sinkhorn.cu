@@ -424,6 +424,7 @@ int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const
   DKD_REQUIRE(Ds == 192 && Dt == kD, DKD_E_SHAPE, "%s: built for widths 192 -> 384, got %d -> %d", fn, Ds, Dt);
   DKD_REQUIRE(s && t && W && loss && workspace, DKD_E_SHAPE, "%s: null pointer", fn);
   DKD_REQUIRE((((uintptr_t)workspace) & 1023) == 0, DKD_E_ALIGN, "%s: workspace must be 1024-byte aligned", fn);
+  DKD_REQUIRE((((uintptr_t)s | (uintptr_t)t | (uintptr_t)g_s) & 31) == 0, DKD_E_ALIGN, "%s: s, t and g_s must be 32-byte aligned (256-bit accesses)", "dkd_wass_sinkhorn_fwdbwd");
   DKD_REQUIRE(B * 6 < (1ll << 24), DKD_E_SHAPE, "%s: too many samples", fn);
   const int P = precision == DKD_PREC_BF16X3 ? 2 : 1;
   const int64_t M = B * kTok;

@@ -88,6 +88,22 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// shared -> global tensor stores (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent store groups of this thread have finished READING shared memory
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// ... have completed (global writes performed)
+template <int N> __device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- TMEM ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -182,5 +198,8 @@ __device__ __forceinline__ void term_planes(int term, int nterms, int& pa, int& 
 // ---- host: tensor maps (driver entry point resolved at run time; no link-time libcuda) --------
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const char* what);
+// general form: elt_bytes 2 (bf16) | 4 (fp32); swizzle_bytes 128 | 64 (inner box bytes must not exceed it)
+int make_tmap(CUtensorMap* out, const void* base, int elt_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, const char* what);
 
 }  // namespace dkd

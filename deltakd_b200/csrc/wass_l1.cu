@@ -14,9 +14,7 @@
 //        sign(diff) goes back through shared memory so the +-1 gradient plane is written with full rows.
 //   5-6. g_s = c * G W, g_W = c * G^T S, g_b = c * G^T 1  (tcgen05; c = scale folded into the epilogues)
 // The sort is on-chip (shared memory + registers): HBM traffic is the a/t tile reads and the +-1 plane write.
-#include "epilogues.cuh"
-#include "gemm_nt.cuh"
-#include "planes.cuh"
+#include "align_ops.cuh"
 
 namespace dkd {
 namespace {
@@ -229,10 +227,6 @@ __global__ void __launch_bounds__(kSortThreads) wass_sort_kernel(SortParams p) {
   }
 }
 
-using FwdCfg = GemmCfg<192, 1, 4, 2>;
-using DgradCfg = GemmCfg<192, 1, 4, 2>;
-using WgradCfg = GemmNtCfg<3, true, 208, 0, 4>;
-
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
@@ -279,6 +273,7 @@ int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float
   DKD_REQUIRE(Ds == 192 && Dt == 384, DKD_E_SHAPE, "%s: built for widths 192 -> 384, got %d -> %d", fn, Ds, Dt);
   DKD_REQUIRE(s && t && W && loss && workspace, DKD_E_SHAPE, "%s: null pointer", fn);
   DKD_REQUIRE((((uintptr_t)workspace) & 1023) == 0, DKD_E_ALIGN, "%s: workspace must be 1024-byte aligned", fn);
+  DKD_REQUIRE((((uintptr_t)s | (uintptr_t)t | (uintptr_t)g_s) & 31) == 0, DKD_E_ALIGN, "%s: s, t and g_s must be 32-byte aligned (256-bit accesses)", "dkd_wass_l1_fwdbwd");
   const int P = precision == DKD_PREC_BF16X3 ? 2 : 1;
   const int64_t M = B * n_tok;
   DKD_REQUIRE(M < (1ll << 31) - 256 && B * (Dt / kCh) < (1ll << 31), DKD_E_SHAPE, "%s: too many rows", fn);
@@ -286,33 +281,14 @@ int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float
   DKD_REQUIRE(workspace_bytes >= ws.bytes, DKD_E_WORKSPACE, "%s: workspace %zu < %zu", fn, workspace_bytes, ws.bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool want_grads = g_s || g_W || g_b;
-  const int nterms = P == 2 ? 3 : 1;
 
   rc = launch_tokens_to_planes(s, dtype, B, Ts, s_off, n_tok, Ds, P, nullptr, ws.S, st);
   if (rc != DKD_OK) return rc;
   rc = launch_weight_to_planes(W, Dt, Ds, P, ws.Wp, want_grads ? ws.Wt : nullptr, st);
   if (rc != DKD_OK) return rc;
 
-  {  // a = S W^T + b, fp32 rows
-    using Cfg = FwdCfg;
-    using L = PlaneLoader<Cfg>;
-    using E = StoreRowsEpi<Cfg>;
-    GemmParams<L, E> p;
-    rc = make_plane_tmap(&p.ld.tmA, ws.S, P, M, Ds, Ds, M * Ds, Cfg::BM, "wass S");
-    if (rc != DKD_OK) return rc;
-    rc = make_plane_tmap(&p.ld.tmB, ws.Wp, P, Dt, Ds, Ds, (int64_t)Dt * Ds, Cfg::BN, "wass W");
-    if (rc != DKD_OK) return rc;
-    p.ld.k_blocks = Ds / 64; p.ld.nterms = nterms;
-    p.ep.out = ws.A; p.ep.drop_mask = nullptr; p.ep.bias = bias; p.ep.alpha = 1.f;
-    p.ep.M = M; p.ep.N_total = Dt; p.ep.n_tok = (int)M; p.ep.T_out = (int)M; p.ep.off = 0; p.ep.out_is_bf16 = 0;
-    p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM); p.n_tiles = Dt / Cfg::BN;
-    const int grid = min(kNumSMs, p.m_tiles * p.n_tiles);
-    auto kern = gemm_tn_kernel<Cfg, L, E>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
-    rc = check_launch("dkd_wass_l1_fwdbwd: align GEMM");
-    if (rc != DKD_OK) return rc;
-  }
+  rc = align_forward_rows(ws.S, ws.Wp, bias, ws.A, M, Ds, Dt, P, st, "dkd_wass_l1_fwdbwd: align GEMM");   // a = S W^T + b
+  if (rc != DKD_OK) return rc;
   const int sort_grid = (int)(B * (Dt / kCh));
   {
     SortParams sp;
@@ -330,50 +306,12 @@ int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float
   if (!want_grads) return DKD_OK;
 
   if (g_s) {  // g_s = scale * G W
-    using Cfg = DgradCfg;
-    using L = PlaneLoader<Cfg>;
-    using E = StoreRowsEpi<Cfg>;
-    GemmParams<L, E> p;
-    rc = make_plane_tmap(&p.ld.tmA, ws.G, P, M, Dt, Dt, M * Dt, Cfg::BM, "wass G");
-    if (rc != DKD_OK) return rc;
-    rc = make_plane_tmap(&p.ld.tmB, ws.Wt, P, Ds, Dt, Dt, (int64_t)Dt * Ds, Cfg::BN, "wass W^T");
-    if (rc != DKD_OK) return rc;
-    p.ld.k_blocks = Dt / 64; p.ld.nterms = nterms;
-    p.ep.out = g_s; p.ep.drop_mask = nullptr; p.ep.bias = nullptr; p.ep.alpha = scale;
-    p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off; p.ep.out_is_bf16 = dtype == DKD_BF16;
-    p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM); p.n_tiles = Ds / Cfg::BN;
-    const int grid = min(kNumSMs, p.m_tiles * p.n_tiles);
-    auto kern = gemm_tn_kernel<Cfg, L, E>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
-    rc = check_launch("dkd_wass_l1_fwdbwd: dgrad GEMM");
+    rc = align_dgrad(ws.G, ws.Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, dtype == DKD_BF16, scale, st, "dkd_wass_l1_fwdbwd: dgrad GEMM");
     if (rc != DKD_OK) return rc;
   }
   if (g_W || g_b) {
-    using Cfg = WgradCfg;
-    using L = NtPlainLoader<Cfg>;
     DKD_REQUIRE(g_W != nullptr, DKD_E_UNSUPPORTED, "%s: g_b without g_W is not supported", fn);
-    GemmNtParamsT<Cfg, L> p;
-    rc = make_plane_tmap(&p.ld.tmA, ws.G, P, M, Dt, Dt, M * Dt, Cfg::KROWS, "wass G^T");
-    if (rc != DKD_OK) return rc;
-    rc = make_plane_tmap(&p.ld.tmB, ws.S, P, M, Ds, Ds, M * Ds, Cfg::KROWS, "wass S (wgrad)");
-    if (rc != DKD_OK) return rc;
-    rc = make_plane_tmap(&p.ld.tmOnes, ws.ones, 2, 64, 64, 64, 64 * 64, Cfg::KROWS, "ones tile");
-    if (rc != DKD_OK) return rc;
-    rc = launch_fill_ones_tile(ws.ones, st);
-    if (rc != DKD_OK) return rc;
-    cudaMemsetAsync(g_W, 0, (size_t)Dt * Ds * sizeof(float), st);
-    if (g_b) cudaMemsetAsync(g_b, 0, (size_t)Dt * sizeof(float), st);
-    p.ep.D = g_W; p.ep.Dcol = g_b; p.ep.ldd = Ds; p.ep.alpha = scale;
-    p.ld.ldd = Ds; p.ld.na_tiles = Dt / 128; p.ld.b_col0 = 0;
-    p.ld.total_row_blocks = (int)((M + Cfg::KROWS - 1) / Cfg::KROWS);
-    nt_make_splits(p.ld.total_row_blocks, kNumSMs / p.ld.na_tiles, &p.ld.splits, &p.ld.row_blocks_per_split);
-    p.nterms = nterms;
-    const int grid = min(kNumSMs, p.ld.na_tiles * p.ld.splits);
-    auto kern = gemm_nt_kernel<Cfg, L>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
-    rc = check_launch("dkd_wass_l1_fwdbwd: wgrad GEMM");
+    rc = align_wgrad(ws.G, ws.S, ws.ones, g_W, g_b, M, Ds, Dt, P, scale, st, "dkd_wass_l1_fwdbwd: wgrad GEMM");
     if (rc != DKD_OK) return rc;
   }
   return DKD_OK;
