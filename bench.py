@@ -417,8 +417,143 @@ class MGDBf16(MGD):
     tdtype = torch.bfloat16
 
 
+class DeiTKDStep(Workload):
+    """End-to-end DeiT-Tiny distillation step (SURVEY 8d "End-to-end"; BASELINE metric "DeiT-Ti KD step img/s"):
+    student deit_tiny_distilled fwd (bf16 autocast) -> DistillationLoss (frozen deit_small_distilled teacher forward
+    inside, once) -> backward -> fused AdamW, DDP gradient all-reduce over NCCL when world > 1.  The models are the
+    plain-PyTorch harness of deltakd_b200/deit.py (timm is absent; model code is outside the hot path), random init,
+    synthetic ImageNet-shaped inputs.  Timed eagerly (no CUDA graph): the step contains the optimizer and DDP."""
+    name = "deit_tiny_kd_step_soft_b256_bf16"
+    dtype = "bf16"
+    B, kind = 256, "soft"
+    student_name = "deit_tiny_distilled_patch16_224"
+    bound = "tensor"
+    graphable = False
+    default_steps = 10
+    cpu_B = 8
+    dominant = "whole step: torch model code (cuBLAS / SDPA) + deltakd loss kernels"
+
+    def bytes_per_set(self):
+        return self.B * 3 * 224 * 224 * 4 + self.B * 1000 * 4
+
+    def nsets(self):
+        return 2
+
+    def algorithmic_flops(self):   # DeiT paper MACs: student 1.3 G fwd (x3 for fwd+bwd), teacher 4.6 G fwd
+        return self.B * 2.0 * (3 * 1.3e9 + 4.6e9)
+
+    def host_sets(self, n, B=None):
+        B = B or self.B
+        sets = []
+        for i in range(n):
+            g = torch.Generator().manual_seed(1234 + self.rank + 17 * i)
+            x = torch.randn(B, 3, 224, 224, generator=g)
+            y = torch.softmax(torch.randn(B, 1000, generator=g), dim=-1)
+            sets.append((_pin(x), _pin(y)))
+        return sets
+
+    def make_args(self):
+        from deltakd_b200 import synth
+        return synth.default_args(distillation_type=self.kind, current_epoch=0)
+
+    def _build(self, device):
+        from deltakd_b200 import DistillationLoss, call_base_loss, deit, heads as H
+        args = self.make_args()
+        torch.manual_seed(0)
+        teacher = deit.create_model("deit_small_distilled_patch16_224").to(device).eval()
+        for p_ in teacher.parameters():
+            p_.requires_grad_(False)
+        student = deit.create_model(self.student_name).to(device)
+        H.attach_distillation_heads(student, teacher, args, self.student_name)
+        student = student.to(device).train()
+        return args, teacher, student, DistillationLoss, call_base_loss
+
+    def setup(self):
+        import torch.distributed as dist
+        self.args, self.teacher, self.student, DL, cbl = self._build(self.device)
+        self.model = self.student
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.model = torch.nn.parallel.DistributedDataParallel(self.student, device_ids=[self.device.index],
+                                                                   find_unused_parameters=self.kind != "soft")
+        self.crit = DL(cbl(self.args), _Autocast(self.teacher), self.kind, 0.1, 3.0)
+        self.opt = torch.optim.AdamW(self.student.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+
+    def to_device(self, hs):
+        return tuple(t.to(self.device, non_blocking=True) for t in hs)
+
+    def h2d_bytes(self):
+        return self.bytes_per_set()
+
+    def step(self, ds):
+        from deltakd_b200 import forward_with_features
+        x, y = ds
+        self.opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if self.kind in ("soft", "hard"):
+                out, feats = self.model(x), None
+            else:
+                out, feats = forward_with_features(self.model, x)
+        loss = self.crit(x, out, self.model, feats, y, self.args)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    op_only = step
+
+    def cpu_prepare(self, hs):
+        return hs
+
+    def cpu_step(self, cs):
+        """Reference-style CPU step: same harness models in fp32 on the host, oracle loss (the reference's arithmetic)."""
+        from oracle import losses as O
+        from deltakd_b200 import heads as H, features
+        if not hasattr(self, "_cpu"):
+            args, teacher, student, _, _ = self._build(torch.device("cpu"))
+            self._cpu = (args, teacher, student, torch.optim.AdamW(student.parameters(), lr=5e-4, weight_decay=0.05))
+        args, teacher, student, opt = self._cpu
+        x, y = cs
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            if self.kind in ("soft", "hard"):
+                t_logits, t_feats = teacher(x), None
+            else:
+                t_logits, t_feats = features.forward_with_features(teacher, x)
+        if self.kind in ("soft", "hard"):
+            out, s_feats = student(x), None
+        else:
+            out, s_feats = features.forward_with_features(student, x)
+        l = O.distillation_loss(self.kind, out, y, t_logits, s_feats, t_feats, H.head_tensors(student), args, 0.1, 3.0)
+        l.backward()
+        opt.step()
+        return l
+
+
+class _Autocast(torch.nn.Module):
+    """Runs the frozen teacher under bf16 autocast (the reference runs it in fp32, twice)."""
+
+    def __init__(self, inner):
+        super().__init__()
+        self.inner = inner
+        self.embed_dim = inner.embed_dim
+
+    @property
+    def blocks(self):
+        return self.inner.blocks
+
+    def forward(self, x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return self.inner(x)
+
+
+class DeiTKDStepCurKD(DeiTKDStep):
+    """The same end-to-end step with the CurKD early-phase feature loss (layers 0-2 hidden-state matching)."""
+    name = "deit_tiny_kd_step_curkd_b256_bf16"
+    kind = "curkd"
+    student_name = "deit_tiny_patch16_224"
+
+
 HEADLINE = LogitKD
-EXTRAS = (LogitKDLargeBatch, CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16, SaliencyMGD, LRKD, WassL1, WassSinkhorn)
+EXTRAS = (DeiTKDStep, DeiTKDStepCurKD, LogitKDLargeBatch, CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16, SaliencyMGD, LRKD, WassL1, WassSinkhorn)
 WORKLOADS = {w.name: w for w in (HEADLINE,) + EXTRAS}
 
 
@@ -509,21 +644,36 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
         w.step(dsets[i % nsets])
     torch.cuda.synchronize()
     c0 = _lib.lib.dkd_launch_count()
-    graph, last = _graph_of(lambda i: w.step(dsets[(W + i) % nsets]), K)
-    launches = (_lib.lib.dkd_launch_count() - c0) * K // (K + 1)   # the capture pass ran fn K+1 times
-    ms, win = _timed_replay(graph, barrier)
-    windows.append(win)
-    loss_val = float(last.item())
-    del graph
+    if getattr(w, "graphable", True):
+        graph, last = _graph_of(lambda i: w.step(dsets[(W + i) % nsets]), K)
+        launches = (_lib.lib.dkd_launch_count() - c0) * K // (K + 1)   # the capture pass ran fn K+1 times
+        ms, win = _timed_replay(graph, barrier)
+        windows.append(win)
+        loss_val = float(last.item())
+        del graph
 
-    # ---- the fused loss op alone (C-ABI call without the autograd rescale), same rotation, own graph
-    with torch.no_grad():
-        pass
-    kg, _ = _graph_of(lambda i: w.op_only(dsets[(W + i) % nsets]), K)
-    k_ms, win = _timed_replay(kg, barrier)
-    windows.append(win)
-    k_ms /= K
-    del kg
+        # ---- the fused loss op alone (C-ABI call without the autograd rescale), same rotation, own graph
+        kg, _ = _graph_of(lambda i: w.op_only(dsets[(W + i) % nsets]), K)
+        k_ms, win = _timed_replay(kg, barrier)
+        windows.append(win)
+        k_ms /= K
+        del kg
+    else:   # eager: K steps between two events (the step holds an optimizer and, multi-GPU, DDP's all-reduce)
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(K):
+            last = w.step(dsets[(W + i) % nsets])
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        windows.append((t0, time.time()))
+        ms = e0.elapsed_time(e1)
+        launches = _lib.lib.dkd_launch_count() - c0
+        loss_val = float(last.item())
+        k_ms = ms / K
 
     # ---- end to end through the public API with host buffers
     for i in range(W):
@@ -557,6 +707,8 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
                      "kernel": w.dominant, "kernel_us": k_ms * 1e3, "peak_source": pk["src"],
                      ("algorithmic_bytes" if w.bound == "hbm" else "algorithmic_flops"): alg},
     }
+    if not getattr(w, "graphable", True):
+        res["timing"] = "eager steps (optimizer + DDP inside), CUDA events, max over ranks"
     if w.bound == "hbm" and w.algorithmic_flops():
         res["roofline"]["algorithmic_flops"] = w.algorithmic_flops()
     if hasattr(w, "extra_roofline"):
@@ -630,8 +782,9 @@ def main():
             "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
             "config": {"workload": head["workload"], "batch_per_gpu": head["batch_per_gpu"],
-                       "timing": "CUDA-graph replay of K steps, CUDA events, max over ranks", "l2": head["l2"],
-                       "teacher": "teacher outputs replayed (inputs of the loss path)", "loss": head["loss"]},
+                       "timing": head.get("timing", "CUDA-graph replay of K steps, CUDA events, max over ranks"), "l2": head["l2"],
+                       "teacher": ("frozen DeiT-Small teacher forward inside the step" if "deit" in head["workload"]
+                                   else "teacher outputs replayed (inputs of the loss path)"), "loss": head["loss"]},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": clocks,
         }
         if "cpu_baseline" in head:

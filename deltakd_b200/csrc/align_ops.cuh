@@ -11,13 +11,14 @@
 
 namespace dkd {
 
-using AlignFwdCfg = GemmCfg<192, 1, 4, 2>;
-using AlignDgradCfg = GemmCfg<192, 1, 4, 2>;
-using AlignWgradCfg = GemmNtCfg<3, true, 208, 0, 4>;
+using AlignCfg1 = GemmCfg<192, 1, 4, 2>;            // one plane per stage (bf16 operands), 4-stage ring
+using AlignCfg2 = GemmCfg<192, 1, 2, 2, 128, 2>;    // both planes per stage (bf16x3), 2 stages of 80 KB
+using AlignWgradCfg1 = GemmNtCfg<3, true, 208, 0, 4>;
+using AlignWgradCfg2 = GemmNtCfg<3, true, 208, 0, 2, 64, false, 2>;   // both planes per stage: 2 stages of 96 KB
 
-inline int align_forward_rows(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, float* A, int64_t M, int Ds, int Dt,
-                              int P, cudaStream_t st, const char* what) {
-  using Cfg = AlignFwdCfg;
+template <class Cfg>
+inline int align_forward_rows_t(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, float* A, int64_t M, int Ds, int Dt,
+                                int P, cudaStream_t st, const char* what) {
   using L = PlaneLoader<Cfg>;
   using E = StoreRowsEpi<Cfg>;
   GemmParams<L, E> p;
@@ -38,10 +39,10 @@ inline int align_forward_rows(const __nv_bfloat16* S, const __nv_bfloat16* Wp, c
 
 // d = S W^T + bias - t[:, t_off:] ; per-CTA loss partials ; G = gscale * d as planes (teacher read in place).
 // `grid_out` = number of partials written.
-inline int align_forward_residual(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, const void* t, int t_is_bf16,
-                                  int Tt, int t_off, int n_tok, __nv_bfloat16* G, double* partials, float gscale, int64_t M, int Ds,
-                                  int Dt, int P, cudaStream_t st, int* grid_out, const char* what) {
-  using Cfg = AlignFwdCfg;
+template <class Cfg>
+inline int align_forward_residual_t(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, const void* t, int t_is_bf16,
+                                    int Tt, int t_off, int n_tok, __nv_bfloat16* G, double* partials, float gscale, int64_t M, int Ds,
+                                    int Dt, int P, cudaStream_t st, int* grid_out, const char* what) {
   using L = PlaneLoader<Cfg>;
   using E = ResidualMseEpi<Cfg>;
   GemmParams<L, E> p;
@@ -62,9 +63,9 @@ inline int align_forward_residual(const __nv_bfloat16* S, const __nv_bfloat16* W
   return check_launch(what);
 }
 
-inline int align_dgrad(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* g_s, int64_t M, int n_tok, int Ts, int s_off, int Ds, int Dt,
-                       int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what) {
-  using Cfg = AlignDgradCfg;
+template <class Cfg>
+inline int align_dgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* g_s, int64_t M, int n_tok, int Ts, int s_off, int Ds, int Dt,
+                         int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what) {
   using L = PlaneLoader<Cfg>;
   using E = StoreRowsEpi<Cfg>;
   GemmParams<L, E> p;
@@ -83,9 +84,28 @@ inline int align_dgrad(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* g_
   return check_launch(what);
 }
 
-inline int align_wgrad(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bfloat16* ones, float* g_W, float* g_b, int64_t M, int Ds, int Dt,
-                       int P, float alpha, cudaStream_t st, const char* what) {
-  using Cfg = AlignWgradCfg;
+inline int align_forward_rows(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, float* A, int64_t M, int Ds, int Dt,
+                              int P, cudaStream_t st, const char* what) {
+  return P == 2 ? align_forward_rows_t<AlignCfg2>(S, Wp, bias, A, M, Ds, Dt, P, st, what)
+                : align_forward_rows_t<AlignCfg1>(S, Wp, bias, A, M, Ds, Dt, P, st, what);
+}
+inline int align_forward_residual(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, const void* t, int t_is_bf16,
+                                  int Tt, int t_off, int n_tok, __nv_bfloat16* G, double* partials, float gscale, int64_t M, int Ds,
+                                  int Dt, int P, cudaStream_t st, int* grid_out, const char* what) {
+  return P == 2 ? align_forward_residual_t<AlignCfg2>(S, Wp, bias, t, t_is_bf16, Tt, t_off, n_tok, G, partials, gscale, M, Ds, Dt, P, st,
+                                                      grid_out, what)
+                : align_forward_residual_t<AlignCfg1>(S, Wp, bias, t, t_is_bf16, Tt, t_off, n_tok, G, partials, gscale, M, Ds, Dt, P, st,
+                                                      grid_out, what);
+}
+inline int align_dgrad(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* g_s, int64_t M, int n_tok, int Ts, int s_off, int Ds, int Dt,
+                       int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what) {
+  return P == 2 ? align_dgrad_t<AlignCfg2>(G, Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, out_is_bf16, alpha, st, what)
+                : align_dgrad_t<AlignCfg1>(G, Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, out_is_bf16, alpha, st, what);
+}
+
+template <class Cfg>
+inline int align_wgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bfloat16* ones, float* g_W, float* g_b, int64_t M, int Ds, int Dt,
+                         int P, float alpha, cudaStream_t st, const char* what) {
   using L = NtPlainLoader<Cfg>;
   GemmNtParamsT<Cfg, L> p;
   int rc = make_plane_tmap(&p.ld.tmA, G, P, M, Dt, Dt, M * Dt, Cfg::KROWS, what);
@@ -108,6 +128,12 @@ inline int align_wgrad(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bflo
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
   return check_launch(what);
+}
+
+inline int align_wgrad(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bfloat16* ones, float* g_W, float* g_b, int64_t M, int Ds, int Dt,
+                       int P, float alpha, cudaStream_t st, const char* what) {
+  return P == 2 ? align_wgrad_t<AlignWgradCfg2>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what)
+                : align_wgrad_t<AlignWgradCfg1>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what);
 }
 
 }  // namespace dkd

@@ -15,8 +15,11 @@
 
 namespace dkd {
 
-template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64, bool A_KMAJOR_ = false>
+// PLANES_ = 2: a stage holds both bf16 planes of the A and B blocks and the three bf16x3 products are issued from it
+// (each operand byte is fetched once instead of 1.5 times); the caller passes nterms = 3.
+template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64, bool A_KMAJOR_ = false, int PLANES_ = 1>
 struct GemmNtCfg {
+  static constexpr int PLANES = PLANES_;
   static constexpr bool A_KMAJOR = A_KMAJOR_;       // A tile is [128 rows x 64 k] K-major (one box) instead of two MN-major boxes
   static constexpr int NA = 128;                      // UMMA M
   static constexpr int NB_BOXES = NB_BOXES_;          // 64-column boxes of B data
@@ -29,7 +32,7 @@ struct GemmNtCfg {
   static constexpr int BOX_BYTES = KROWS_ * 128;
   static constexpr int A_BYTES = 2 * BOX_BYTES;
   static constexpr int B_BYTES = (NB_BOXES_ + (ONES_ ? 1 : 0)) * BOX_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = PLANES_ * (A_BYTES + B_BYTES);
   static constexpr int STAGES = STAGES_;
   static constexpr int TMEM_COLS = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : NB <= 256 ? 256 : 512;
   static constexpr int THREADS = 192;
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)Cfg::STAGES * Cfg::A_BYTES;
+  constexpr int A_STAGE = Cfg::PLANES * Cfg::A_BYTES, B_STAGE = Cfg::PLANES * Cfg::B_BYTES;
+  uint8_t* sB = smem + (size_t)Cfg::STAGES * A_STAGE;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty = full + Cfg::STAGES;
   uint64_t* acc_full = empty + Cfg::STAGES;
@@ -98,12 +102,22 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         typename Loader::Item it;
         Loader::decode(p.ld, item, it);
-        for (int term = 0; term < p.nterms; ++term) {
+        if constexpr (Cfg::PLANES == 2) {
           for (int rb = it.rb0; rb < it.rb1; ++rb) {
             mbar_wait(&empty[s], ph ^ 1);
             mbar_expect_tx(&full[s], Loader::TX_BYTES);
-            Loader::issue(p.ld, it, term, p.nterms, rb, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
+            Loader::issue_planes(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
+            Loader::issue_planes(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES, &full[s]);
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+          }
+        } else {
+          for (int term = 0; term < p.nterms; ++term) {
+            for (int rb = it.rb0; rb < it.rb1; ++rb) {
+              mbar_wait(&empty[s], ph ^ 1);
+              mbar_expect_tx(&full[s], Loader::TX_BYTES);
+              Loader::issue(p.ld, it, term, p.nterms, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
+              if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            }
           }
         }
       }
@@ -117,22 +131,28 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         typename Loader::Item it;
         Loader::decode(p.ld, item, it);
-        const int nk = (it.rb1 - it.rb0) * p.nterms;
+        const int nk = (it.rb1 - it.rb0) * (Cfg::PLANES == 2 ? 1 : p.nterms);
         if (nk <= 0) continue;  // (hosts never create empty splits)
         mbar_wait(acc_empty, aph ^ 1);
         tc_fence_after();
         for (int kit = 0; kit < nk; ++kit) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + (size_t)s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + (size_t)s * Cfg::B_BYTES);
+          const uint32_t a_st = smem_u32(sA + (size_t)s * A_STAGE);
+          const uint32_t b_st = smem_u32(sB + (size_t)s * B_STAGE);
+          constexpr int TERMS = Cfg::PLANES == 2 ? 3 : 1;     // (A plane, B plane): (hi,lo) (lo,hi) (hi,hi)
 #pragma unroll
-          for (int k = 0; k < Cfg::KSTEPS; ++k) {  // UMMA_K = 16 rows = 2 groups of 8 rows = 2048 B
-            const uint64_t da = Cfg::A_KMAJOR ? kmajor_desc(a_addr + k * 32) : mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
-            umma_bf16(tmem_base, da, mnmajor_desc(b_addr + k * 2048, Cfg::BOX_BYTES), idesc0, (kit | k) != 0 ? 1u : 0u);
-            if constexpr (Cfg::N1 > 0)
-              umma_bf16(tmem_base + Cfg::N0, da, mnmajor_desc(b_addr + (Cfg::N0 / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES),
-                        idesc1, (kit | k) != 0 ? 1u : 0u);
+          for (int term = 0; term < TERMS; ++term) {
+            const uint32_t a_addr = a_st + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
+            const uint32_t b_addr = b_st + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
+#pragma unroll
+            for (int k = 0; k < Cfg::KSTEPS; ++k) {  // UMMA_K = 16 rows = 2 groups of 8 rows = 2048 B
+              const uint64_t da = Cfg::A_KMAJOR ? kmajor_desc(a_addr + k * 32) : mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
+              umma_bf16(tmem_base, da, mnmajor_desc(b_addr + k * 2048, Cfg::BOX_BYTES), idesc0, (kit | term | k) != 0 ? 1u : 0u);
+              if constexpr (Cfg::N1 > 0)
+                umma_bf16(tmem_base + Cfg::N0, da, mnmajor_desc(b_addr + (Cfg::N0 / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES),
+                          idesc1, (kit | term | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[s]);
           if (kit == nk - 1) umma_commit(acc_full);
@@ -233,6 +253,9 @@ struct NtPlainLoader {
   static __device__ __forceinline__ void issue(const Params& p, const Item& it, int term, int nterms, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
     int pa, pb;
     term_planes(term, nterms, pa, pb);
+    issue_planes(p, it, pa, pb, rb, a, b, bar);
+  }
+  static __device__ __forceinline__ void issue_planes(const Params& p, const Item& it, int pa, int pb, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
     sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
     sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
 #pragma unroll

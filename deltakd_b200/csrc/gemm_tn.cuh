@@ -17,8 +17,12 @@
 
 namespace dkd {
 
-template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128>
+// PLANES_ = 2: a ring stage holds BOTH bf16 planes (hi, lo) of the A and B tiles of one K block and the three
+// bf16x3 products (hi*lo, lo*hi, hi*hi) are issued from it — every operand byte crosses L2 -> shared memory once
+// instead of 1.5 times (the plain scheme replays the K loop per product and re-fetches the hi planes).
+template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128, int PLANES_ = 1>
 struct GemmCfg {
+  static constexpr int PLANES = PLANES_;
   static constexpr int BM = 128;       // UMMA M (cta_group::1)
   static constexpr int TILE_M = TILE_M_;  // rows of the tile that carry data (126 = 9 image rows for the conv loader)
   static constexpr int BN = BN_;       // tile N
@@ -29,7 +33,7 @@ struct GemmCfg {
   static constexpr int ACC = ACC_;
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = PLANES_ * (A_BYTES + B_BYTES);
   static constexpr int TMEM_COLS_USED = ACC * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
   static constexpr int THREADS = 192;
@@ -52,7 +56,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)Cfg::STAGES * Cfg::A_BYTES;
+  constexpr int A_STAGE = Cfg::PLANES * Cfg::A_BYTES, B_STAGE = Cfg::PLANES * Cfg::B_BYTES;
+  uint8_t* sB = smem + (size_t)Cfg::STAGES * A_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
         for (int kit = 0; kit < num_k; ++kit) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], Loader::TX_BYTES);
-          Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * Cfg::A_BYTES, sB + (size_t)s * Cfg::B_BYTES, &full[s]);
+          Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -104,15 +109,21 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
         for (int kit = 0; kit < num_k; ++kit) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + (size_t)s * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + (size_t)s * Cfg::B_BYTES);
+          const uint32_t a_addr = smem_u32(sA + (size_t)s * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + (size_t)s * B_STAGE);
+          constexpr int TERMS = Cfg::PLANES == 2 ? 3 : 1;     // (A plane, B plane): (hi,lo) (lo,hi) (hi,hi) — small terms first
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / 16; ++k) {
-            const uint64_t da = kmajor_desc(a_addr + k * 32);
+          for (int term = 0; term < TERMS; ++term) {
+            const uint32_t a_pl = a_addr + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
+            const uint32_t b_pl = b_addr + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
 #pragma unroll
-            for (int ni = 0; ni < Cfg::NI; ++ni) {
-              const uint64_t db = kmajor_desc(b_addr + ni * Cfg::N_INSTR * 128 + k * 32);
-              umma_bf16(d_tmem + ni * Cfg::N_INSTR, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < Cfg::BK / 16; ++k) {
+              const uint64_t da = kmajor_desc(a_pl + k * 32);
+#pragma unroll
+              for (int ni = 0; ni < Cfg::NI; ++ni) {
+                const uint64_t db = kmajor_desc(b_pl + ni * Cfg::N_INSTR * 128 + k * 32);
+                umma_bf16(d_tmem + ni * Cfg::N_INSTR, da, db, idesc, (kit | term | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty[s]);                       // ring slot reusable once these MMAs retire
@@ -163,19 +174,30 @@ template <class Cfg, int B_BOX_ROWS = (Cfg::BN > 256 ? Cfg::BN / 2 : Cfg::BN)>
 struct PlaneLoader {
   using Params = PlaneLoaderParams;
   static constexpr uint32_t TX_BYTES = Cfg::STAGE_BYTES;
-  static __device__ __forceinline__ int num_k_iters(const Params& p) { return p.k_blocks * p.nterms; }
+  static __device__ __forceinline__ int num_k_iters(const Params& p) { return Cfg::PLANES == 2 ? p.k_blocks : p.k_blocks * p.nterms; }
   static __device__ __forceinline__ void prefetch(const Params& p) {
     sm100::tma_prefetch_desc(&p.tmA);
     sm100::tma_prefetch_desc(&p.tmB);
   }
   static __device__ __forceinline__ void issue(const Params& p, int kit, int mt, int nt, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
-    const int term = kit / p.k_blocks, kb = kit - term * p.k_blocks;
-    int pa, pb;
-    term_planes(term, p.nterms, pa, pb);
-    sm100::tma_load_3d(sA, &p.tmA, bar, kb * 64, mt * Cfg::BM, pa);
+    if constexpr (Cfg::PLANES == 2) {       // both planes of both operands, once per K block
 #pragma unroll
-    for (int i = 0; i < Cfg::BN / B_BOX_ROWS; ++i)
-      sm100::tma_load_3d(sB + (size_t)i * B_BOX_ROWS * 128, &p.tmB, bar, kb * 64, nt * Cfg::BN + i * B_BOX_ROWS, pb);
+      for (int pl = 0; pl < 2; ++pl) {
+        sm100::tma_load_3d(sA + (size_t)pl * Cfg::A_BYTES, &p.tmA, bar, kit * 64, mt * Cfg::BM, pl);
+#pragma unroll
+        for (int i = 0; i < Cfg::BN / B_BOX_ROWS; ++i)
+          sm100::tma_load_3d(sB + (size_t)pl * Cfg::B_BYTES + (size_t)i * B_BOX_ROWS * 128, &p.tmB, bar, kit * 64,
+                             nt * Cfg::BN + i * B_BOX_ROWS, pl);
+      }
+    } else {
+      const int term = kit / p.k_blocks, kb = kit - term * p.k_blocks;
+      int pa, pb;
+      term_planes(term, p.nterms, pa, pb);
+      sm100::tma_load_3d(sA, &p.tmA, bar, kb * 64, mt * Cfg::BM, pa);
+#pragma unroll
+      for (int i = 0; i < Cfg::BN / B_BOX_ROWS; ++i)
+        sm100::tma_load_3d(sB + (size_t)i * B_BOX_ROWS * 128, &p.tmB, bar, kb * 64, nt * Cfg::BN + i * B_BOX_ROWS, pb);
+    }
   }
 };
 

@@ -1,0 +1,106 @@
+"""Minimal DeiT (timm-compatible attribute surface) — BENCH / TEST HARNESS ONLY.
+
+The reference builds its student and teacher with `timm.create_model` (model/models.py:59-75); timm is not in this
+image and the models are outside the hot path (out of scope, plain PyTorch is fine).  This file
+provides random-init stand-ins of `deit_tiny[_distilled]_patch16_224` (192-d, 3 heads) and
+`deit_small_distilled_patch16_224` (384-d, 6 heads) exposing exactly what the loss path touches:
+`.embed_dim`, `.blocks[i].mlp` (hooked by forward_with_features, models.py:185-193), `.head` / `.head_dist`,
+`set_distilled_training` (models.py:97), and timm's output convention (distilled + training + distilled_training
+-> (cls_logits, dist_logits); otherwise their mean / the single head).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+        return self.proj(x.transpose(1, 2).reshape(B, N, C))
+
+
+class Block(nn.Module):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, num_heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class DeiT(nn.Module):
+    def __init__(self, embed_dim: int, depth: int, num_heads: int, num_classes: int = 1000, distilled: bool = False,
+                 img_size: int = 224, patch: int = 16):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.distilled = distilled
+        self.distilled_training = False
+        n = (img_size // patch) ** 2
+        self.patch_embed = nn.Conv2d(3, embed_dim, kernel_size=patch, stride=patch)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim)) if distilled else None
+        self.pos_embed = nn.Parameter(torch.randn(1, n + (2 if distilled else 1), embed_dim) * 0.02)
+        self.blocks = nn.ModuleList([Block(embed_dim, num_heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head = nn.Linear(embed_dim, num_classes)
+        self.head_dist = nn.Linear(embed_dim, num_classes) if distilled else None
+
+    def set_distilled_training(self, enable: bool = True):
+        self.distilled_training = enable
+
+    def forward(self, x):
+        x = self.patch_embed(x).flatten(2).transpose(1, 2)
+        toks = [self.cls_token.expand(x.shape[0], -1, -1)]
+        if self.distilled:
+            toks.append(self.dist_token.expand(x.shape[0], -1, -1))
+        x = torch.cat(toks + [x], dim=1) + self.pos_embed
+        for blk in self.blocks:
+            x = blk(x)
+        x = self.norm(x)
+        if not self.distilled:
+            return self.head(x[:, 0])
+        a, b = self.head(x[:, 0]), self.head_dist(x[:, 1])
+        if self.distilled_training and self.training and not torch.jit.is_scripting():
+            return a, b
+        return (a + b) / 2
+
+
+_ZOO = {
+    "deit_tiny_patch16_224": dict(embed_dim=192, depth=12, num_heads=3, distilled=False),
+    "deit_tiny_distilled_patch16_224": dict(embed_dim=192, depth=12, num_heads=3, distilled=True),
+    "deit_small_patch16_224": dict(embed_dim=384, depth=12, num_heads=6, distilled=False),
+    "deit_small_distilled_patch16_224": dict(embed_dim=384, depth=12, num_heads=6, distilled=True),
+}
+
+
+def create_model(name: str, num_classes: int = 1000, **_) -> DeiT:
+    """Stand-in for timm.create_model(name, pretrained=False, num_classes=...) restricted to the DeiT variants the
+    reference's exp/*.sh scripts use."""
+    if name not in _ZOO:
+        raise ValueError(f"unknown model {name}; available: {sorted(_ZOO)}")
+    return DeiT(num_classes=num_classes, **_ZOO[name])
