@@ -472,11 +472,21 @@ class DeiTKDStep(Workload):
         import torch.distributed as dist
         self.args, self.teacher, self.student, DL, cbl = self._build(self.device)
         self.model = self.student
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.model = torch.nn.parallel.DistributedDataParallel(self.student, device_ids=[self.device.index],
-                                                                   find_unused_parameters=self.kind != "soft")
         self.crit = DL(cbl(self.args), _Autocast(self.teacher), self.kind, 0.1, 3.0)
-        self.opt = torch.optim.AdamW(self.student.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+        # Heads that get no gradient in this phase (CurKD mid/late heads at epoch 0, ...) would stall DDP's reducer
+        # (the reference has this defect): find them with one tiny dry-run step and freeze them.
+        xs = torch.randn(2, 3, 224, 224, device=self.device)
+        ys = torch.softmax(torch.randn(2, 1000, device=self.device), dim=-1)
+        self.opt = None
+        self.step((xs, ys), optimize=False)
+        for p_ in self.student.parameters():
+            if p_.grad is None:
+                p_.requires_grad_(False)
+            p_.grad = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.model = torch.nn.parallel.DistributedDataParallel(self.student, device_ids=[self.device.index])
+        self.opt = torch.optim.AdamW([p_ for p_ in self.student.parameters() if p_.requires_grad], lr=5e-4, weight_decay=0.05,
+                                     fused=True)
 
     def to_device(self, hs):
         return tuple(t.to(self.device, non_blocking=True) for t in hs)
@@ -484,10 +494,11 @@ class DeiTKDStep(Workload):
     def h2d_bytes(self):
         return self.bytes_per_set()
 
-    def step(self, ds):
+    def step(self, ds, optimize=True):
         from deltakd_b200 import forward_with_features
         x, y = ds
-        self.opt.zero_grad(set_to_none=True)
+        if optimize:
+            self.opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             if self.kind in ("soft", "hard"):
                 out, feats = self.model(x), None
@@ -495,7 +506,8 @@ class DeiTKDStep(Workload):
                 out, feats = forward_with_features(self.model, x)
         loss = self.crit(x, out, self.model, feats, y, self.args)
         loss.backward()
-        self.opt.step()
+        if optimize:
+            self.opt.step()
         return loss
 
     op_only = step

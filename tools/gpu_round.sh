@@ -37,5 +37,11 @@ if [[ $STAGES == *n* ]]; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_ -c 12 -f -o $OUT/${TAG}_mgd \
     python bench.py --workload mgd_b512_f32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_mgd.log 2>&1
   echo "ncu mgd rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:wass_sort -c 1 -f -o $OUT/${TAG}_wass_sort \
+    python bench.py --workload wasskd_l1_b512_f32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_wass.log 2>&1
+  echo "ncu wass rc=$?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:sinkhorn_kernel -c 2 -f -o $OUT/${TAG}_sinkhorn \
+    python bench.py --workload wasskd_sinkhorn_b512_f32 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_sink.log 2>&1
+  echo "ncu sinkhorn rc=$?"
   ls -la $OUT/*.ncu-rep
 fi
