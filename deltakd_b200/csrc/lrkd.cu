@@ -9,9 +9,9 @@
 //   2. Gram  G = T^T T  on tcgen05 (gemm_nt, split over rows, 6 plane products = fp32-exact operands); each split
 //      stores its fp32 partial tile, a second kernel adds the partials in fp64 in a fixed order (deterministic),
 //      symmetrises and puts the exact diagonal in
-//   3. eigenvectors of G: one-sided (Hestenes) Jacobi in fp64, all layers batched in ONE cooperative launch:
-//      192 warps per matrix rotate 192 disjoint column pairs per round (round-robin ordering), matrix resident in L2,
-//      one grid barrier per round; stops when every pair is orthogonal to 1e-10
+//   3. eigenvectors of G: one-sided (Hestenes) Jacobi in fp64, all layers batched in ONE cooperative launch, two-level
+//      ordering: 12 CTAs per matrix each sweep a pair of 16-column groups in shared memory (31 inner rounds), one grid
+//      barrier per group round (23 per sweep); stops when every rotated pair is orthogonal to 1e-10
 //   4. select: column norms = eigenvalues, rank them (descending, ties by index), V_k = top-k normalised columns;
 //      builds the fused operand [W' | -V_k] (bf16 hi/lo planes) and the transposed head for the backward
 //   5. d = [s | T] [W' | -V_k]^T + b' = s' - A  in ONE tcgen05 GEMM (K = Ds + Dt), epilogue: loss partial and
@@ -28,10 +28,15 @@ namespace dkd {
 namespace {
 
 constexpr int kN = 384;              // Dt: order of the Gram matrix
-constexpr int kJacobiCtas = 24;      // per matrix: 24 CTAs x 8 warps = 192 pairs per round
-constexpr int kJacobiThreads = 256;
+constexpr int kJacobiGroup = 16;     // columns per group
+constexpr int kJacobiCtas = kN / kJacobiGroup / 2;   // 12 CTAs per matrix, each owns a pair of groups per outer round
+constexpr int kJacobiThreads = 512;  // 16 warps = 16 column pairs per inner round
+constexpr size_t kJacobiSmem = (size_t)2 * kJacobiGroup * kN * sizeof(double);   // 96 KB
 constexpr int kMaxSweeps = 14;
-constexpr double kJacobiTol = 1e-10;
+constexpr double kJacobiTol = 1e-10;   // pairs with |cos| below this are not rotated
+// Jacobi converges quadratically: a sweep that SAW no |cos| above 1e-6 leaves the columns orthogonal to ~1e-12, so it
+// is the last one (no separate verification sweep).
+constexpr double kJacobiStop = 1e-6;
 constexpr int kMaxLayers = 8;
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -155,16 +160,25 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// Two-level (block) one-sided Jacobi.  The 384 columns form 24 groups of 16; in an outer round every CTA owns a pair
+// of groups (round-robin tournament over the groups: 23 outer rounds per sweep), copies its 32 columns (96 KB of fp64)
+// into shared memory, rotates the 16 x 16 cross pairs there (16 inner rounds, 16 warps = 16 disjoint column pairs per
+// inner round, __syncthreads between rounds; the pairs inside a group are done once per sweep, in outer round 0) and
+// writes them back.  One grid barrier per OUTER round: 23 per sweep instead of the 383 of a flat ordering — the
+// solver is bound by the latency of its sequential rounds, not by arithmetic.
 __global__ void __launch_bounds__(kJacobiThreads) jacobi_kernel(JacobiParams p) {
-  constexpr int n = kN, PER = n / 32;  // 12 elements per lane
+  constexpr int n = kN, PER = n / 32;          // 12 elements per lane
+  constexpr int G = kJacobiGroup, NG = n / G;  // 16 columns per group, 24 groups
+  constexpr int LC = 2 * G;                    // 32 columns per CTA
+  extern __shared__ double scol[];             // [LC][n]
   const int layer = blockIdx.y;
   double* W = p.W + (size_t)layer * n * n;
   unsigned* bar = p.bar + layer;
   unsigned long long* offmax = p.offmax + 2 * layer;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pairi = blockIdx.x * (kJacobiThreads / 32) + warp;   // 0 .. 191
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // 16 warps
   // columns whose norm is below 1e-13 * trace(G) belong to the null space (rank-deficient teacher): never rotated
   __shared__ double s_tiny;
+  __shared__ double s_off[kJacobiThreads / 32];
   if (warp == 0) {
     double tr = 0.0;
     for (int i = lane; i < n; i += 32) tr += W[(size_t)i * n + i];
@@ -177,46 +191,80 @@ __global__ void __launch_bounds__(kJacobiThreads) jacobi_kernel(JacobiParams p) 
   int sweep = 0;
   for (; sweep < kMaxSweeps; ++sweep) {
     double local_off = 0.0;
-    for (int r = 0; r < n - 1; ++r) {
-      // round-robin tournament: position 0 is fixed, the others rotate; pair = (pos i, pos n-1-i)
-      const int pi = pairi, pj = n - 1 - pairi;
-      const int cp = pi == 0 ? 0 : 1 + (pi - 1 + r) % (n - 1);
-      const int cq = 1 + (pj - 1 + r) % (n - 1);
-      double* a = W + (size_t)cp * n;
-      double* b = W + (size_t)cq * n;
-      double x[PER], y[PER];
-      double aa = 0.0, bb = 0.0, ab = 0.0;
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        x[k] = __ldcg(a + lane + 32 * k);
-        y[k] = __ldcg(b + lane + 32 * k);
+    for (int r = 0; r < NG - 1; ++r) {
+      // round-robin tournament over groups: position 0 is fixed, the others rotate; this CTA takes (pos c, pos NG-1-c)
+      const int pi = blockIdx.x, pj = NG - 1 - blockIdx.x;
+      const int gp = pi == 0 ? 0 : 1 + (pi - 1 + r) % (NG - 1);
+      const int gq = 1 + (pj - 1 + r) % (NG - 1);
+      for (int idx = threadIdx.x; idx < LC * n; idx += kJacobiThreads) {
+        const int c = idx / n, i = idx - c * n;
+        const int gc = (c < G ? gp * G : gq * G - G) + c;
+        scol[idx] = __ldcg(W + (size_t)gc * n + i);
       }
+      __syncthreads();
+      // inner rounds: in outer round 0 first the pairs INSIDE each of the two groups (15 rounds, 8 pairs per group),
+      // then — every outer round — the 16 x 16 cross pairs (16 rounds of 16 disjoint pairs).  Per sweep every column
+      // pair is rotated exactly once: 23 * 16 + 15 = 383 sequential rounds, as in a flat ordering, but 360 of the
+      // 383 synchronisations are __syncthreads instead of grid barriers.
+      const int n_inner = (r == 0 ? G - 1 : 0) + G;
+      for (int ir = 0; ir < n_inner; ++ir) {
+        int cp, cq;
+        if (r == 0 && ir < G - 1) {            // within-group tournament: warps 0-7 group P, warps 8-15 group Q
+          const int base = (warp >> 3) * G, w8 = warp & 7;
+          const int qi = w8, qj = G - 1 - w8;
+          cp = base + (qi == 0 ? 0 : 1 + (qi - 1 + ir) % (G - 1));
+          cq = base + 1 + (qj - 1 + ir) % (G - 1);
+        } else {
+          const int k = ir - (r == 0 ? G - 1 : 0);
+          cp = warp;
+          cq = G + ((warp + k) & (G - 1));
+        }
+        double* a = scol + cp * n;
+        double* b = scol + cq * n;
+        double x[PER], y[PER];
+        double aa = 0.0, bb = 0.0, ab = 0.0;
 #pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        aa = fma(x[k], x[k], aa); bb = fma(y[k], y[k], bb); ab = fma(x[k], y[k], ab);
+        for (int k = 0; k < PER; ++k) { x[k] = a[lane + 32 * k]; y[k] = b[lane + 32 * k]; }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { aa = fma(x[k], x[k], aa); bb = fma(y[k], y[k], bb); ab = fma(x[k], y[k], ab); }
+        aa = warp_sum_d(aa); bb = warp_sum_d(bb); ab = warp_sum_d(ab);
+        const double prod = aa * bb;
+        const double cosv = (prod > 0.0 && (aa > tiny || bb > tiny)) ? fabs(ab) * rsqrt(prod) : 0.0;
+        local_off = fmax(local_off, cosv);
+        if (cosv > kJacobiTol) {
+          // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (bb - aa) / (2 ab), written with one division:
+          // t = sign(d h) |h| / (|d| + sqrt(d^2 + h^2)), d = bb - aa, h = 2 ab ;  c = 1/sqrt(1 + t^2), s = c t
+          const double d = bb - aa, h = 2.0 * ab;
+          const double t = ((d >= 0.0) == (h >= 0.0) ? fabs(h) : -fabs(h)) / (fabs(d) + sqrt(fma(d, d, h * h)));
+          const double c = rsqrt(fma(t, t, 1.0)), sn = c * t;
+#pragma unroll
+          for (int k = 0; k < PER; ++k) {
+            a[lane + 32 * k] = c * x[k] - sn * y[k];
+            b[lane + 32 * k] = sn * x[k] + c * y[k];
+          }
+        }
+        __syncthreads();
       }
-      aa = warp_sum_d(aa); bb = warp_sum_d(bb); ab = warp_sum_d(ab);
-      const double denom = sqrt(aa * bb);
-      const double cosv = (denom > 0.0 && (aa > tiny || bb > tiny)) ? fabs(ab) / denom : 0.0;
-      local_off = fmax(local_off, cosv);
-      if (cosv > kJacobiTol) {
-        const double zeta = (bb - aa) / (2.0 * ab);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-          const double nx = c * x[k] - s * y[k], ny = s * x[k] + c * y[k];
-          a[lane + 32 * k] = nx;
-          b[lane + 32 * k] = ny;
+      for (int idx = threadIdx.x; idx < LC * n; idx += kJacobiThreads) {
+        const int c = idx / n, i = idx - c * n;
+        const int gc = (c < G ? gp * G : gq * G - G) + c;
+        W[(size_t)gc * n + i] = scol[idx];
+      }
+      if (r == NG - 2) {   // end of the sweep: publish this CTA's largest |cos|
+        if (lane == 0) s_off[warp] = local_off;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double m = 0.0;
+          for (int w = 0; w < kJacobiThreads / 32; ++w) m = fmax(m, s_off[w]);
+          atomicMax(offmax + (sweep & 1), (unsigned long long)__double_as_longlong(m));
         }
       }
-      if (r == n - 2 && lane == 0) atomicMax(offmax + (sweep & 1), (unsigned long long)__double_as_longlong(local_off));
       ++epoch;
       layer_barrier(bar, epoch * gridDim.x);
       if (r == 0 && blockIdx.x == 0 && threadIdx.x == 0) offmax[(sweep + 1) & 1] = 0ull;  // buffer of the next sweep
     }
     const double off = __longlong_as_double((long long)__ldcg(offmax + (sweep & 1)));
-    if (off <= kJacobiTol) { ++sweep; break; }
+    if (off <= kJacobiStop) { ++sweep; break; }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.sweeps_out) p.sweeps_out[layer] = sweep;
 }
@@ -473,7 +521,9 @@ int dkd_lrkd_fwdbwd(int n_layers, const void* const* s, const void* const* t, co
     JacobiParams jp;
     jp.W = ws.W; jp.bar = ws.bar; jp.offmax = ws.offmax; jp.sweeps_out = sweeps_out;
     void* kargs[] = {&jp};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)jacobi_kernel, dim3(kJacobiCtas, n_layers), dim3(kJacobiThreads), kargs, 0, st);
+    cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJacobiSmem);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)jacobi_kernel, dim3(kJacobiCtas, n_layers), dim3(kJacobiThreads), kargs,
+                                                kJacobiSmem, st);
     if (e != cudaSuccess) {
       set_error("%s: cooperative launch of the Jacobi eigensolver failed: %s", fn, cudaGetErrorString(e));
       cudaGetLastError();
