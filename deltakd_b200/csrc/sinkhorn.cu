@@ -13,7 +13,7 @@
 //   6.   Sinkhorn loops, cost matrix resident in shared memory (one bulk copy), potentials in registers:
 //        xy kernel — one CTA per pair, a thread per row (f_ba) and a thread per column (g_ab) of C_xy;
 //        sym kernel — one CTA per (pair, xx | yy), a thread per row.  Softmins are base-2 log-sum-exps
-//        (two passes: max, then MUFU ex2).  The last (extrapolation) step also emits the transport plans
+//        (one pass per step: online maximum + MUFU ex2; the symmetric problems use two threads per row).  The last (extrapolation) step also emits the transport plans
 //        P = softmax_j(h_b - C_xy/eps), Q = softmax_j(h_a - C_xx/eps) as bf16 hi/lo planes.
 //   7.   g_a = scale/N (Q x - P y): batched tcgen05 GEMM (K-major plans x MN-major points), written as planes
 //   8-9. g_s = g_a W, g_W = g_a^T s, g_b = g_a^T 1 (align_ops.cuh)
@@ -25,8 +25,10 @@ namespace {
 
 constexpr int kTok = 196;                   // points per cloud (14 x 14 patch tokens)
 constexpr int kD = 384;                     // teacher width
-constexpr int kLD = 204;                    // cost-matrix row pitch in floats: 16-byte rows, conflict-free LDS.128 per row-thread
-constexpr int kCostBytes = kTok * kLD * 4;  // 159 936
+constexpr int kLD = 204;                    // allocation pitch of a cost matrix in floats (and the pitch of C_xy)
+constexpr int kLDxy = 204;                  // C_xy: one thread per row -> 8 consecutive rows hit 8 distinct 16-byte bank groups
+constexpr int kLDsym = 200;                 // C_xx, C_yy: two threads per row -> (row, half) pairs hit distinct bank groups
+constexpr int kCostBytes = kTok * kLD * 4;  // 159 936 (copied whole; the symmetric matrices use the first 196*200 floats)
 constexpr int kLDP = 208;                   // plan row pitch in bf16 (416 B)
 constexpr int kMaxEps = 64;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -142,7 +144,7 @@ struct CostEpi {
     const float* na = (which == 2 ? p.ny : p.nx) + (size_t)pair * kTok;
     const float* nb = (which == 1 ? p.nx : p.ny) + (size_t)pair * kTok;
     const float ni = live ? __ldg(na + i) : 0.f;
-    float* out = p.C + ((size_t)(pair * 3 + which) * kTok + (live ? i : 0)) * kLD;
+    float* out = p.C + (size_t)(pair * 3 + which) * kTok * kLD + (size_t)(live ? i : 0) * (which == 0 ? kLDxy : kLDsym);
 #pragma unroll 1
     for (int c0 = 0; c0 < 192; c0 += 32) {
       float v[32];
@@ -199,56 +201,71 @@ __device__ __forceinline__ void load_cost(float* sC, const float* gC, uint64_t* 
   mbar_wait(bar, 0);
 }
 
-// base-2 log-sum-exp over row i:  log2 sum_j 2^(h[j] - C[i][j]*c2); returns it and (optionally) leaves max / sum
-__device__ __forceinline__ float lse2_row(const float* __restrict__ crow, const float* __restrict__ h, float c2, float& m_out, float& s_out) {
+// One-pass ("online") base-2 log-sum-exp.  Values v_j = h[j] - C[.][j]*c2 are produced in chunks of up to 28; the
+// running maximum m and the sum s = sum 2^(v - m) are rescaled when a chunk raises the maximum (one extra ex2 per
+// chunk) — each cost entry is read from shared memory once per eps step instead of twice.
+struct Lse { float m, s; };
+__device__ __forceinline__ void lse_push(Lse& a, const float (&v)[28], int cnt) {
+  float cm = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 28; ++q) if (q < cnt) cm = fmaxf(cm, v[q]);
+  const float mn = fmaxf(a.m, cm);
+  float s0 = a.s * ex2f(a.m - mn), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 28; q += 4) {
+    if (q + 0 < cnt) s0 += ex2f(v[q + 0] - mn);
+    if (q + 1 < cnt) s1 += ex2f(v[q + 1] - mn);
+    if (q + 2 < cnt) s2 += ex2f(v[q + 2] - mn);
+    if (q + 3 < cnt) s3 += ex2f(v[q + 3] - mn);
+  }
+  a.m = mn; a.s = (s0 + s1) + (s2 + s3);
+}
+// float4 chunks [k0, k1) of one row
+__device__ __forceinline__ Lse lse2_row_part(const float* __restrict__ crow, const float* __restrict__ h, float c2, int k0, int k1) {
   const float4* c4 = reinterpret_cast<const float4*>(crow);
   const float4* h4 = reinterpret_cast<const float4*>(h);
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 7
-  for (int k = 0; k < kTok / 4; ++k) {
-    const float4 c = c4[k], hh = h4[k];
-    m0 = fmaxf(m0, fmaf(-c.x, c2, hh.x)); m1 = fmaxf(m1, fmaf(-c.y, c2, hh.y));
-    m2 = fmaxf(m2, fmaf(-c.z, c2, hh.z)); m3 = fmaxf(m3, fmaf(-c.w, c2, hh.w));
+  Lse a{-INFINITY, 0.f};
+#pragma unroll 1
+  for (int kb = k0; kb < k1; kb += 7) {
+    const int n4 = min(7, k1 - kb);
+    float v[28];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      if (q < n4) {
+        const float4 c = c4[kb + q], hh = h4[kb + q];
+        v[4 * q] = fmaf(-c.x, c2, hh.x); v[4 * q + 1] = fmaf(-c.y, c2, hh.y);
+        v[4 * q + 2] = fmaf(-c.z, c2, hh.z); v[4 * q + 3] = fmaf(-c.w, c2, hh.w);
+      }
+    }
+    lse_push(a, v, 4 * n4);
   }
-  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 7
-  for (int k = 0; k < kTok / 4; ++k) {
-    const float4 c = c4[k], hh = h4[k];
-    s0 += ex2f(fmaf(-c.x, c2, hh.x) - m); s1 += ex2f(fmaf(-c.y, c2, hh.y) - m);
-    s2 += ex2f(fmaf(-c.z, c2, hh.z) - m); s3 += ex2f(fmaf(-c.w, c2, hh.w) - m);
+  return a;
+}
+// whole column j of C_xy (stride kLDxy; consecutive threads -> consecutive banks)
+__device__ __forceinline__ Lse lse2_col(const float* __restrict__ ccol, const float* __restrict__ h, float c2) {
+  Lse a{-INFINITY, 0.f};
+#pragma unroll 1
+  for (int i0 = 0; i0 < kTok; i0 += 28) {
+    float v[28];
+#pragma unroll
+    for (int q = 0; q < 28; ++q) v[q] = fmaf(-ccol[(i0 + q) * kLDxy], c2, h[i0 + q]);
+    lse_push(a, v, 28);
   }
-  const float s = (s0 + s1) + (s2 + s3);
-  m_out = m; s_out = s;
-  return m + __log2f(s);
+  return a;
+}
+__device__ __forceinline__ Lse lse_merge(const Lse& a, const Lse& b) {
+  const float m = fmaxf(a.m, b.m);
+  return Lse{m, a.s * ex2f(a.m - m) + b.s * ex2f(b.m - m)};
 }
 
-// ... and over column j (stride kLD; consecutive threads -> consecutive banks)
-__device__ __forceinline__ float lse2_col(const float* __restrict__ ccol, const float* __restrict__ h, float c2) {
-  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 7
-  for (int i = 0; i < kTok; i += 4) {
-    m0 = fmaxf(m0, fmaf(-ccol[(i + 0) * kLD], c2, h[i + 0])); m1 = fmaxf(m1, fmaf(-ccol[(i + 1) * kLD], c2, h[i + 1]));
-    m2 = fmaxf(m2, fmaf(-ccol[(i + 2) * kLD], c2, h[i + 2])); m3 = fmaxf(m3, fmaf(-ccol[(i + 3) * kLD], c2, h[i + 3]));
-  }
-  const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 7
-  for (int i = 0; i < kTok; i += 4) {
-    s0 += ex2f(fmaf(-ccol[(i + 0) * kLD], c2, h[i + 0]) - m); s1 += ex2f(fmaf(-ccol[(i + 1) * kLD], c2, h[i + 1]) - m);
-    s2 += ex2f(fmaf(-ccol[(i + 2) * kLD], c2, h[i + 2]) - m); s3 += ex2f(fmaf(-ccol[(i + 3) * kLD], c2, h[i + 3]) - m);
-  }
-  return m + __log2f((s0 + s1) + (s2 + s3));
-}
-
-// plan row i:  sign * 2^(h[j] - C[i][j]*c2 - m) / s  as bf16 hi / lo, 4 entries (8 bytes) per store
-__device__ __forceinline__ void write_plan_row(const float* __restrict__ crow, const float* __restrict__ h, float c2, float m, float s,
-                                               float sign, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+// plan row segment:  sign * 2^(h[j] - C[i][j]*c2 - m) / s  as bf16 hi / lo, float4 chunks [k0, k1), 8-byte stores
+__device__ __forceinline__ void write_plan_part(const float* __restrict__ crow, const float* __restrict__ h, float c2, float m, float s,
+                                                float sign, __nv_bfloat16* hi, __nv_bfloat16* lo, int k0, int k1) {
   const float4* c4 = reinterpret_cast<const float4*>(crow);
   const float4* h4 = reinterpret_cast<const float4*>(h);
   const float inv = sign / s;
-#pragma unroll 7
-  for (int k = 0; k < kTok / 4; ++k) {
+#pragma unroll 5
+  for (int k = k0; k < k1; ++k) {
     const float4 c = c4[k], hh = h4[k];
     float v[4], r[4];
     v[0] = inv * ex2f(fmaf(-c.x, c2, hh.x) - m); v[1] = inv * ex2f(fmaf(-c.y, c2, hh.y) - m);
@@ -260,19 +277,24 @@ __device__ __forceinline__ void write_plan_row(const float* __restrict__ crow, c
   }
 }
 
-constexpr int kRoleThreads = 224;   // 7 warps per role, 196 of them active
+constexpr int kRoleThreads = 224;   // xy kernel: 7 warps per role (rows | columns), 196 threads of each active
+constexpr int kSymThreads = 416;    // symmetric kernel: two threads per row (392 active)
 constexpr size_t kSinkSmem = (size_t)kCostBytes + 4 * kTok * sizeof(float) + 64;
 
 // Step schedule (geomloss sinkhorn_loop): step -1 initialises the potentials at eps[0] from the log-weights alone,
 // steps 0..n-1 average (symmetric update) at eps[k], step n is the final extrapolation at eps[n-1] (plain assignment).
+//   XY  : one CTA per pair, cost C_xy; thread i < 196 of role 0 owns row i (f_ba), thread j of role 1 column j (g_ab)
+//   !XY : one CTA per (pair, xx | yy); threads 2i, 2i+1 own the two halves of row i (f_aa or g_bb)
 template <bool XY>
-__global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kRoleThreads, 1) sinkhorn_kernel(SinkParams p) {
+__global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kSymThreads, 1) sinkhorn_kernel(SinkParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* sC = reinterpret_cast<float*>(smem_raw);
   float* hR = sC + kTok * kLD;            // [2][196] : h over columns j, read by the row threads
   float* hC = hR + 2 * kTok;              // [2][196] : h over rows i, read by the column threads (xy only)
   uint64_t* bar = reinterpret_cast<uint64_t*>(hC + 2 * kTok);
-  __shared__ double red[2 * kRoleThreads / 32];
+  __shared__ double red[16];
+  constexpr int LD = XY ? kLDxy : kLDsym;
+  constexpr int K4 = kTok / 4;            // 49 float4 chunks per row
 
   const int pair = XY ? blockIdx.x : blockIdx.x >> 1;
   const int which = XY ? 0 : 1 + (blockIdx.x & 1);
@@ -281,34 +303,46 @@ __global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kRoleThreads, 1) sinkh
   const int n = p.n_eps[pair];
   const float* eps_list = p.eps + (size_t)pair * kMaxEps;
   const bool is_col = XY && threadIdx.x >= kRoleThreads;
-  const int idx = is_col ? threadIdx.x - kRoleThreads : threadIdx.x;   // row i or column j
+  const int idx = XY ? (is_col ? threadIdx.x - kRoleThreads : threadIdx.x) : threadIdx.x >> 1;   // row i or column j
+  const int half = XY ? 0 : threadIdx.x & 1;
+  const int k0 = XY ? 0 : (half ? 25 : 0), k1 = XY ? K4 : (half ? K4 : 25);   // this thread's float4 chunks of its row
   const bool active = idx < kTok;
   const float logw = -__logf((float)kTok);
-  float pot = 0.f;            // f_ba[i] / g_ab[j] (xy) or f_aa[i] / g_bb[i] (sym)
-  float m_fin = 0.f, s_fin = 1.f, c2_fin = 0.f;
+  float pot = 0.f;            // f_ba[i] / g_ab[j] (xy) or f_aa[i] / g_bb[i] (sym; both halves hold the same value)
+  Lse fin{0.f, 1.f};
+  float c2_fin = 0.f;
 
   for (int step = -1; step <= n; ++step) {
     const float eps = eps_list[step < 0 ? 0 : (step < n ? step : n - 1)];
     const int buf = (step + 1) & 1;
     // this thread's potential becomes an entry of the h vector the OTHER role reads (same role for the symmetric problems)
-    if (active) {
+    if (active && half == 0) {
       const float hv = (logw + (step < 0 ? 0.f : pot / eps)) * kLog2e;
       if (XY) (is_col ? hR : hC)[buf * kTok + idx] = hv;
       else hR[buf * kTok + idx] = hv;
     }
     __syncthreads();
+    const float c2 = kLog2e / eps;
+    Lse a{0.f, 1.f};
     if (active) {
-      const float c2 = kLog2e / eps;
-      float l2;
-      if (is_col) l2 = lse2_col(sC + idx, hC + buf * kTok, c2);
-      else { l2 = lse2_row(sC + idx * kLD, hR + buf * kTok, c2, m_fin, s_fin); c2_fin = c2; }
-      const float upd = -eps * kLn2 * l2;
+      if (is_col) a = lse2_col(sC + idx, hC + buf * kTok, c2);
+      else a = lse2_row_part(sC + idx * LD, hR + buf * kTok, c2, k0, k1);
+    }
+    if (!XY) {   // the two halves of a row sit in adjacent lanes
+      Lse o;
+      o.m = __shfl_xor_sync(0xffffffffu, a.m, 1);
+      o.s = __shfl_xor_sync(0xffffffffu, a.s, 1);
+      a = lse_merge(a, o);
+    }
+    if (active) {
+      if (!is_col) { fin = a; c2_fin = c2; }
+      const float upd = -eps * kLn2 * (a.m + __log2f(a.s));
       pot = (step < 0 || step == n) ? upd : 0.5f * (pot + upd);
     }
   }
 
   // divergence partial: xy -> +(sum f_ba + sum g_ab)/N ; xx, yy -> -(sum f)/N
-  double acc = active ? (double)pot : 0.0;
+  double acc = (active && half == 0) ? (double)pot : 0.0;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -322,7 +356,7 @@ __global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kRoleThreads, 1) sinkh
     const int mat = XY ? 1 : 0;
     const size_t plane = (size_t)p.pairs * kTok * kLDP;
     __nv_bfloat16* hi = p.plans + ((size_t)mat * 2 * p.pairs + pair) * kTok * kLDP + (size_t)idx * kLDP;
-    write_plan_row(sC + idx * kLD, hR + ((n + 1) & 1) * kTok, c2_fin, m_fin, s_fin, XY ? -1.f : 1.f, hi, hi + plane);
+    write_plan_part(sC + idx * LD, hR + ((n + 1) & 1) * kTok, c2_fin, fin.m, fin.s, XY ? -1.f : 1.f, hi, hi + plane, k0, k1);
   }
 }
 
@@ -487,7 +521,7 @@ int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const
     sinkhorn_kernel<true><<<pairs, 2 * kRoleThreads, kSinkSmem, st>>>(sp);
     rc = check_launch("dkd_wass_sinkhorn_fwdbwd: sinkhorn xy");
     if (rc != DKD_OK) return rc;
-    sinkhorn_kernel<false><<<pairs * 2, kRoleThreads, kSinkSmem, st>>>(sp);
+    sinkhorn_kernel<false><<<pairs * 2, kSymThreads, kSinkSmem, st>>>(sp);
     rc = check_launch("dkd_wass_sinkhorn_fwdbwd: sinkhorn xx/yy");
     if (rc != DKD_OK) return rc;
     rc = launch_fold_partials(ws.partials, pairs * 3, scale, loss, st);
