@@ -136,6 +136,21 @@ __device__ __forceinline__ void stg256(__nv_bfloat16* p, const float (&v)[16]) {
                : "memory");
 }
 
+// 32 consecutive fp32 of a small read-only vector (bias, mask token): every thread of the warp reads the same
+// 128 bytes, so 8 broadcast 16-byte loads replace 32 scalar ones.  `p` may be null (-> zeros).
+__device__ __forceinline__ void ldg_vec32(const float* p, float (&x)[32]) {
+  if (p == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = 0.f;
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p) + j);
+    x[4 * j] = w.x; x[4 * j + 1] = w.y; x[4 * j + 2] = w.z; x[4 * j + 3] = w.w;
+  }
+}
+
 // fp32 x[32] -> bf16 hi (and lo = x - hi) planes, 64 contiguous bytes each
 __device__ __forceinline__ void store_planes32(__nv_bfloat16* hi_ptr, int64_t plane_stride, int planes, float (&x)[32]) {
   stg256(hi_ptr, *reinterpret_cast<float(*)[16]>(&x[0]));

@@ -103,16 +103,18 @@ struct ConvEpi {
       }
       sm100::tmem_ld_wait();
       if (!live) continue;
+      float bs[32];   // bias of this chunk, or the mask token for masked rows of the mask-fill epilogue
+      if (MODE == EPI_MASKFILL && mk != 0.f) ldg_vec32(p.mask_token + n0 + c0, bs);
+      else if (MODE == EPI_RELU || MODE == EPI_MSE || MODE == EPI_MASKFILL) ldg_vec32(p.bias ? p.bias + n0 + c0 : nullptr, bs);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int c = n0 + c0 + j;
         float x = v[j];
-        if (MODE == EPI_RELU) x = fmaxf(x + __ldg(p.bias + c), 0.f);
-        if (MODE == EPI_MASKFILL) x = mk != 0.f ? __ldg(p.mask_token + c) : x + (p.bias ? __ldg(p.bias + c) : 0.f);
+        if (MODE == EPI_RELU) x = fmaxf(x + bs[j], 0.f);
+        if (MODE == EPI_MASKFILL) x = mk != 0.f ? bs[j] : x + bs[j];
         if (MODE == EPI_DRELU) x = aux[j] > 0.f ? x : 0.f;
         if (MODE == EPI_MSE) {
           if (mk != 0.f) {
-            const float d = x + __ldg(p.bias + c) - aux[j];
+            const float d = x + bs[j] - aux[j];
             st.acc = fmaf(d, d, st.acc);
             x = p.gscale * d;
           } else {

@@ -8,12 +8,12 @@ namespace dkd {
 __device__ __forceinline__ void load_act32(const void* base, int64_t elem_off, int is_bf16, float (&x)[32]) {
   if (is_bf16) {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + elem_off;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::load(p + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
+    ldg256(p, *reinterpret_cast<float(*)[16]>(&x[0]));
+    ldg256(p + 16, *reinterpret_cast<float(*)[16]>(&x[16]));
   } else {
     const float* p = reinterpret_cast<const float*>(base) + elem_off;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) Vec<float, 4>::load(p + 4 * j, *reinterpret_cast<float(*)[4]>(&x[4 * j]));
+    for (int j = 0; j < 4; ++j) ldg256(p + 8 * j, *reinterpret_cast<float(*)[8]>(&x[8 * j]));
   }
 }
 
@@ -66,10 +66,11 @@ struct ResidualMseEpi {
     sm100::tmem_ld32(t_addr, v);
     sm100::tmem_ld_wait();
     if (live) {
-      float hi[32], lo[32];
+      float hi[32], lo[32], bs[32];
+      ldg_vec32(p.bias ? p.bias + col : nullptr, bs);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float d = v[j] + (p.bias ? __ldg(p.bias + col + j) : 0.f) - tv[j];
+        const float d = v[j] + bs[j] - tv[j];
         st.acc = fmaf(d, d, st.acc);
         const float g = p.gscale * d;
         hi[j] = g;
@@ -146,8 +147,10 @@ struct StoreRowsEpi {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       } else {
+        float bs[32];
+        ldg_vec32(p.bias ? p.bias + n0 + c0 : nullptr, bs);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * p.alpha + bs[j];
       }
       float z[32];
 #pragma unroll
