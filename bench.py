@@ -135,12 +135,13 @@ class LogitKD(Workload):
         return 6 * self.B * self.C * self.tdtype.itemsize
 
     def host_sets(self, n, B=None):
+        """One pinned [4, B, C] buffer per set (outputs, outputs_kd, teacher logits, soft labels): a single H2D copy."""
         from deltakd_b200 import synth
         B = B or self.B
         sets = []
         for i in range(n):
             z, zk, zt, y = synth.make_logits(B, self.C, 1234 + self.rank + 17 * i)
-            sets.append(tuple(_pin(t.to(self.tdtype)) for t in (z, zk, zt, y)))
+            sets.append(_pin(torch.stack([z, zk, zt, y]).to(self.tdtype)))
         return sets
 
     def setup(self):
@@ -151,8 +152,8 @@ class LogitKD(Workload):
         self.inputs = torch.zeros(self.B, 3, 2, 2, device=self.device)  # images feed only the (replayed) teacher
 
     def to_device(self, hs):
-        z, zk, zt, y = (t.to(self.device, non_blocking=True) for t in hs)
-        return z.requires_grad_(True), zk.requires_grad_(True), zt, y
+        d = hs.to(self.device, non_blocking=True)
+        return d[0].requires_grad_(True), d[1].requires_grad_(True), d[2], d[3]
 
     def h2d_bytes(self):
         return self.bytes_per_set()
@@ -172,7 +173,7 @@ class LogitKD(Workload):
         return Fn.logit_kd_loss(z, zk, zt, y, kd_kind=self.kind, alpha=self.alpha, tau=self.tau)
 
     def cpu_prepare(self, hs):
-        return tuple(t.float() for t in hs)  # the reference runs fp32 end to end
+        return tuple(t.float() for t in hs.unbind(0))  # the reference runs fp32 end to end
 
     def cpu_step(self, cs):
         from oracle import losses as O

@@ -27,7 +27,7 @@ def _run(c):
     return loss
 
 
-@pytest.mark.parametrize("name", ["mgd_r05", "mgd_r03", "curkd_ep200"])
+@pytest.mark.parametrize("name", ["mgd_r05", "mgd_r03", "curkd_ep200", "vitkd"])   # vitkd = 2-layer mimic + generation (loss.py:251-311)
 def test_masked_generation_matches_reference(golden, name):
     c = build_case(name, device="cuda")
     loss = _run(c)
@@ -48,6 +48,8 @@ def test_masked_generation_matches_reference(golden, name):
         checked += 1
     assert checked >= 8  # g_s, align w/b, mask_token, 2 x (conv w, b)
     assert float(c.s_feats[11].grad[:, 0].abs().max()) == 0.0
+    if name == "vitkd":
+        assert c.s_feats[0].grad is not None and c.s_feats[1].grad is not None and c.s_feats[5].grad is None
     if n_flip == 0:  # the reference's recorded gradients (its own gate)
         for tag in ("f32", "f64"):
             for k, p in heads.items():
