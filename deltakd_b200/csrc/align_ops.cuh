@@ -11,8 +11,8 @@
 
 namespace dkd {
 
-using AlignCfg1 = GemmCfg<192, 1, 4, 2>;            // one plane per stage (bf16 operands), 4-stage ring
-using AlignCfg2 = GemmCfg<192, 1, 2, 2, 128, 2>;    // both planes per stage (bf16x3), 2 stages of 80 KB
+using AlignCfg1 = GemmCfg<192, 1, 4, 2, 128, 1, 8>;   // one plane per stage (bf16 operands), 4-stage ring, 8 epilogue warps
+using AlignCfg2 = GemmCfg<192, 1, 2, 2, 128, 2, 8>;   // both planes per stage (bf16x3), 2 stages of 80 KB, 8 epilogue warps
 using AlignWgradCfg1 = GemmNtCfg<3, true, 208, 0, 4>;
 using AlignWgradCfg2 = GemmNtCfg<3, true, 208, 0, 2, 64, false, 2>;   // both planes per stage: 2 stages of 96 KB
 

@@ -18,12 +18,18 @@ __device__ __forceinline__ void load_act32(const void* base, int64_t elem_off, i
 }
 
 // per-CTA fp64 partial of the epilogue threads' fp32 accumulators -> partials[blockIdx.x]
+template <int EPI_WARPS = 4>
 __device__ __forceinline__ void epilogue_block_partial(float acc, int tid, double* partials) {
-  __shared__ double s_part[4];
+  __shared__ double s_part[8];
   double a = warp_sum((double)acc);
   if ((tid & 31) == 0) s_part[tid >> 5] = a;
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-  if (tid == 0) partials[blockIdx.x] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // the epilogue warps only
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < EPI_WARPS; ++w) t += s_part[w];
+    partials[blockIdx.x] = t;
+  }
 }
 
 // *loss += scale * sum(partials[0..n))  — one warp, fixed order (deterministic)
@@ -87,32 +93,31 @@ struct ResidualMseEpi {
     }
   }
 
-  // The teacher chunk of step c+1 is requested before chunk c is processed (two register buffers): each DRAM round
-  // trip overlaps a chunk of TMEM reads, arithmetic and stores instead of being exposed six times per tile.
-  static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc) {
-    static_assert((Cfg::BN / 32) % 2 == 0, "chunks are processed in pairs");
+  // The teacher chunk of the NEXT step is requested before the current chunk is processed (two register buffers):
+  // each DRAM round trip overlaps a chunk of TMEM reads, arithmetic and stores.  With two epilogue groups, group g
+  // takes chunks g, g+2, ...
+  static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc, int group = 0,
+                                              int groups = 1) {
     const int64_t m = (int64_t)m0 + row_in_tile;
     const bool live = m < p.M;
     const int64_t b = live ? m / p.n_tok : 0;
     const int64_t trow = b * p.Tt + p.t_off + (live ? m - b * p.n_tok : 0);
+    const int step = 32 * groups;
     float ta[32], tb[32];
-    load_teacher(p, live, trow, n0, ta);
+    load_teacher(p, live, trow, n0 + group * 32, ta);
 #pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::BN; c0 += 64) {
-      load_teacher(p, live, trow, n0 + c0 + 32, tb);
+    for (int c0 = group * 32; c0 < Cfg::BN; c0 += 2 * step) {
+      if (c0 + step < Cfg::BN) load_teacher(p, live, trow, n0 + c0 + step, tb);
       chunk(p, st, live, m, n0 + c0, t_acc + c0, ta);
-      if (c0 + 64 < Cfg::BN) load_teacher(p, live, trow, n0 + c0 + 64, ta);
-      chunk(p, st, live, m, n0 + c0 + 32, t_acc + c0 + 32, tb);
+      if (c0 + step < Cfg::BN) {
+        if (c0 + 2 * step < Cfg::BN) load_teacher(p, live, trow, n0 + c0 + 2 * step, ta);
+        chunk(p, st, live, m, n0 + c0 + step, t_acc + c0 + step, tb);
+      }
     }
   }
 
   static __device__ __forceinline__ void finish(const Params& p, State& st, int tid) {
-    __shared__ double s_part[4];
-    double a = (double)st.acc;
-    a = warp_sum(a);
-    if ((tid & 31) == 0) s_part[tid >> 5] = a;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-    if (tid == 0) p.partials[blockIdx.x] = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+    epilogue_block_partial<Cfg::EPI_WARPS>(st.acc, tid, p.partials);
   }
 };
 
@@ -131,14 +136,15 @@ struct StoreRowsEpi {
   using Params = StoreRowsParams;
   struct State {};
   static __device__ __forceinline__ void init(const Params&, State&) {}
-  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int n0, int row_in_tile, uint32_t t_acc) {
+  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int n0, int row_in_tile, uint32_t t_acc, int group = 0,
+                                              int groups = 1) {
     const int64_t m = (int64_t)m0 + row_in_tile;
     const bool live = m < p.M;
     const int64_t b = live ? m / p.n_tok : 0;
     const int64_t i = live ? m - b * p.n_tok : 0;
     const int64_t orow = b * p.T_out + p.off + i;
 #pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
+    for (int c0 = group * 32; c0 < Cfg::BN; c0 += 32 * groups) {
       float v[32];
       sm100::tmem_ld32(t_acc + c0, v);
       sm100::tmem_ld_wait();

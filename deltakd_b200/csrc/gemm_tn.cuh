@@ -4,6 +4,7 @@
 //   warp 0      : TMA producer (one elected lane) — fills a STAGES-deep ring of {A 128x64, B BNx64} tiles
 //   warp 1      : TMEM allocation + tcgen05.mma issue (one elected lane), tcgen05.commit frees ring slots
 //   warps 2..5  : epilogue — tcgen05.ld of the accumulator (thread = row), policy-defined math and stores
+//   (warps 6..9 : second epilogue group when Cfg::EPI_WARPS == 8)
 //
 // TMEM holds ACC accumulator stages of BN fp32 columns so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  The fp32-parity mode ("bf16x3") is expressed by the Loader as extra K iterations
@@ -20,9 +21,15 @@ namespace dkd {
 // PLANES_ = 2: a ring stage holds BOTH bf16 planes (hi, lo) of the A and B tiles of one K block and the three
 // bf16x3 products (hi*lo, lo*hi, hi*hi) are issued from it — every operand byte crosses L2 -> shared memory once
 // instead of 1.5 times (the plain scheme replays the K loop per product and re-fetches the hi planes).
-template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128, int PLANES_ = 1>
+// EPI_WARPS_ = 8: two epilogue warps per TMEM lane quadrant (two per scheduler); group g of the two takes the 32-column
+// chunks g, g+2, ... of a tile.  The epilogue is a chain of TMEM reads, DRAM round trips and stores; with a single
+// epilogue warp per scheduler nothing hides those latencies.  Policies used this way take (group, groups) in tile().
+template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128, int PLANES_ = 1, int EPI_WARPS_ = 4>
 struct GemmCfg {
   static constexpr int PLANES = PLANES_;
+  static constexpr int EPI_WARPS = EPI_WARPS_;
+  static constexpr int EPI_GROUPS = EPI_WARPS_ / 4;
+  static_assert(EPI_WARPS_ == 4 || EPI_WARPS_ == 8, "4 or 8 epilogue warps");
   static constexpr int BM = 128;       // UMMA M (cta_group::1)
   static constexpr int TILE_M = TILE_M_;  // rows of the tile that carry data (126 = 9 image rows for the conv loader)
   static constexpr int BN = BN_;       // tile N
@@ -36,7 +43,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = PLANES_ * (A_BYTES + B_BYTES);
   static constexpr int TMEM_COLS_USED = ACC * BN;
   static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
-  static constexpr int THREADS = 192;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS_;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(N_INSTR % 16 == 0 && N_INSTR >= 16 && N_INSTR <= 256, "UMMA N");
   static_assert(TMEM_COLS_USED <= 512, "TMEM columns");
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < Cfg::ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int a = 0; a < Cfg::ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], Cfg::EPI_WARPS); }
     fence_barrier_init();
     Loader::prefetch(p.ld);
   }
@@ -145,7 +152,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Cfg::BN);
-      Epi::tile(p.ep, st, mt * Cfg::TILE_M, nt * Cfg::BN, row_in_tile, t_acc);
+      if constexpr (Cfg::EPI_GROUPS > 1) Epi::tile(p.ep, st, mt * Cfg::TILE_M, nt * Cfg::BN, row_in_tile, t_acc, (warp - 2) >> 2, Cfg::EPI_GROUPS);
+      else Epi::tile(p.ep, st, mt * Cfg::TILE_M, nt * Cfg::BN, row_in_tile, t_acc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);

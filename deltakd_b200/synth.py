@@ -96,6 +96,10 @@ class FeatureReplayModel(nn.Module):
 
     def set_outputs(self, logits, feats):
         self.logits = logits
+        self._has_feats = feats is not None
+        if feats is None and not getattr(self, "_feats_set", False):
+            return                                  # logits-only replay: nothing to reset
+        self._feats_set = feats is not None
         for blk, f in zip(self.blocks, feats if feats is not None else [None] * len(self.blocks)):
             blk.mlp.value = f
 
@@ -103,6 +107,7 @@ class FeatureReplayModel(nn.Module):
         self.distilled_training = enable
 
     def forward(self, x):
-        for blk in self.blocks:
-            blk.mlp(x)
+        if getattr(self, "_has_feats", True):       # the hooks only matter when block outputs are replayed
+            for blk in self.blocks:
+                blk.mlp(x)
         return self.logits
