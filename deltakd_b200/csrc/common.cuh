@@ -188,6 +188,7 @@ __device__ __forceinline__ void block_sum(float (&v)[K], float* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  if constexpr (THREADS == 32) return;   // a single warp owns the data: no shared memory, no barrier
   __syncthreads();  // protect scratch reuse
   if (lane == 0) {
 #pragma unroll
@@ -208,6 +209,7 @@ __device__ __forceinline__ void block_max(float (&v)[K], float* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) v[k] = warp_max(v[k]);
+  if constexpr (THREADS == 32) return;
   __syncthreads();
   if (lane == 0) {
 #pragma unroll

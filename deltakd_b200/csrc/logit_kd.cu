@@ -14,6 +14,15 @@ namespace {
 
 constexpr int kThreads = 128;
 
+// e^x through MUFU.EX2 (2 instructions instead of expf's ~20).  Arguments here are <= 0 (maximum subtracted) and O(10):
+// the relative error (~2^-22 plus the rounding of x*log2(e)) is ~1e-6, far inside the 1e-5 / 1e-4 parity gates —
+// and with ~100 instructions per logit the exact expf made the kernel issue-bound instead of HBM-bound.
+__device__ __forceinline__ float fexp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 struct LogitKdParams {
   const void* z;      // outputs
   const void* zk;     // outputs_kd
@@ -31,40 +40,41 @@ struct LogitKdParams {
 };
 
 // NV > 0: row cached in registers (C <= kThreads*VEC*NV).  NV == 0: streaming (re-read) path.
-template <typename T, int VEC, int NV>
-__global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
-  __shared__ float scratch[8 * (kThreads / 32)];
-  __shared__ int s_arg[kThreads / 32];
-  __shared__ float s_argv[kThreads / 32];
-  __shared__ bool s_last;
-
-  const int64_t row = blockIdx.x;
+// One batch row: block-reduced maxima / sums, both gradient rows written, per-row loss partials stored.
+// z / zk / zt / y point at the row's operands — in global memory (one CTA per row) or in a shared-memory stage
+// filled by bulk copies (streaming kernel below); the arithmetic is the same code.
+template <typename T, int VEC, int NV, int THREADS = kThreads>
+__device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, const T* z, const T* zk, const T* zt, const T* y,
+                                          float* scratch, int* s_arg, float* s_argv) {
   const int64_t C = p.C;
-  const T* z = p.label_kind >= 0 ? reinterpret_cast<const T*>(p.z) + row * C : nullptr;
-  const T* zk = p.kd_kind ? reinterpret_cast<const T*>(p.zk) + row * C : nullptr;
-  const T* zt = p.kd_kind ? reinterpret_cast<const T*>(p.zt) + row * C : nullptr;
-  const T* y = p.label_kind == 0 ? reinterpret_cast<const T*>(p.y) + row * C : nullptr;
+  const int tid = THREADS == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;   // THREADS == 32: one warp per row
   const int64_t label = p.label_kind == 1 ? reinterpret_cast<const int64_t*>(p.y)[row] : -1;
   const float invT = p.kd_kind == 1 ? 1.f / p.tau : 1.f;
 
   constexpr int NVR = NV > 0 ? NV : 1;
   float rz[NVR][VEC], rk[NVR][VEC], rt[NVR][VEC], ry[NVR][VEC];
-  const int nchunk = (int)((C + (int64_t)kThreads * VEC - 1) / ((int64_t)kThreads * VEC));
+  const int nchunk = (int)((C + (int64_t)THREADS * VEC - 1) / ((int64_t)THREADS * VEC));
 
-  auto col_of = [&](int it) -> int64_t { return ((int64_t)it * kThreads + threadIdx.x) * VEC; };
+  auto col_of = [&](int it) -> int64_t { return ((int64_t)it * THREADS + tid) * VEC; };
+  // Loads are unconditional and branch-free: columns past the row end are clamped to column 0 (the passes test
+  // col < C themselves), and operands a mode does not use alias one it does (their values are never read; the
+  // duplicate loads hit L1).  Kernel-uniform branches on the mode split the loads into basic blocks, each exposing
+  // its own DRAM round trip (ncu: six equal long-scoreboard stalls per row); this way they issue back to back.
+  const T* any = p.label_kind >= 0 ? z : zk;
+  const T* lz = p.label_kind >= 0 ? z : any;
+  const T* lzk = p.kd_kind ? zk : any;
+  const T* lzt = p.kd_kind ? zt : any;
+  const T* ly = p.label_kind == 0 ? y : any;
   auto load4 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
-    const int64_t col = col_of(it);
-    if (col < C) {  // C % VEC == 0 by construction
-      if (p.label_kind >= 0) Vec<T, VEC>::load(z + col, a);
-      else {
+    const int64_t col0 = col_of(it);
+    const int64_t col = col0 < C ? col0 : 0;  // C % VEC == 0 by construction
+    Vec<T, VEC>::load(lz + col, a);
+    Vec<T, VEC>::load(lzk + col, b);
+    Vec<T, VEC>::load(lzt + col, c);
+    Vec<T, VEC>::load(ly + col, d);
+    if (p.label_kind < 0) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) a[v] = 0.f;
-      }
-      if (p.kd_kind) {
-        Vec<T, VEC>::load(zk + col, b);
-        Vec<T, VEC>::load(zt + col, c);
-      }
-      if (p.label_kind == 0) Vec<T, VEC>::load(y + col, d);
+      for (int v = 0; v < VEC; ++v) a[v] = 0.f;
     }
   };
 
@@ -87,20 +97,20 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
     }
   };
   if constexpr (NV > 0) {
+    // all of the row's loads are issued before the first value is used: one DRAM round trip per row, not one per chunk
 #pragma unroll
-    for (int it = 0; it < NV; ++it) {
-      if (it < nchunk) {
-        load4(it, rz[it], rk[it], rt[it], ry[it]);
-        pass1(it, rz[it], rk[it], rt[it]);
-      }
-    }
+    for (int it = 0; it < NV; ++it)
+      if (it < nchunk) load4(it, rz[it], rk[it], rt[it], ry[it]);
+#pragma unroll
+    for (int it = 0; it < NV; ++it)
+      if (it < nchunk) pass1(it, rz[it], rk[it], rt[it]);
   } else {
     for (int it = 0; it < nchunk; ++it) {
       load4(it, rz[0], rk[0], rt[0], ry[0]);
       pass1(it, rz[0], rk[0], rt[0]);
     }
   }
-  block_max<3, kThreads>(mx, scratch);
+  block_max<3, THREADS>(mx, scratch);
   int64_t tgt = label;  // index whose one-hot enters the KD gradient (hard) -- label handled separately
   int64_t hard_idx = -1;
   if (p.kd_kind == 2) {
@@ -113,13 +123,15 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
       long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { s_argv[threadIdx.x >> 5] = bv; s_arg[threadIdx.x >> 5] = (int)bi; }
-    __syncthreads();
-    bv = s_argv[0]; bi = s_arg[0];
+    if constexpr (THREADS > 32) {
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { s_argv[threadIdx.x >> 5] = bv; s_arg[threadIdx.x >> 5] = (int)bi; }
+      __syncthreads();
+      bv = s_argv[0]; bi = s_arg[0];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) {
-      if (s_argv[w] > bv || (s_argv[w] == bv && s_arg[w] < bi)) { bv = s_argv[w]; bi = s_arg[w]; }
+      for (int w = 1; w < THREADS / 32; ++w) {
+        if (s_argv[w] > bv || (s_argv[w] == bv && s_arg[w] < bi)) { bv = s_argv[w]; bi = s_arg[w]; }
+      }
     }
     hard_idx = bi;
   }
@@ -138,20 +150,20 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
     if (col < C) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float ea = expf(a[v] - mx[0]);
+        const float ea = fexp(a[v] - mx[0]);
         s[0] += ea;
         if (p.label_kind == 0) { t[0] += d[v]; t[1] += d[v] * a[v]; }
         else { t[1] += a[v]; if (col + v == label) t[2] = a[v]; }
         if (NV > 0) a[v] = ea;
         if (p.kd_kind == 1) {
           const float av = b[v] * invT, bv = c[v] * invT;
-          const float eb = expf(bv - mx[2]), es = expf(av - mx[1]);
+          const float eb = fexp(bv - mx[2]), es = fexp(av - mx[1]);
           s[1] += es;
           s[2] += eb;
           s[3] += eb * (bv - av);
           if (NV > 0) { b[v] = es; c[v] = eb; }
         } else if (p.kd_kind == 2) {
-          const float es = expf(b[v] - mx[1]);
+          const float es = fexp(b[v] - mx[1]);
           s[1] += es;
           if (col + v == hard_idx) t[3] = b[v];
           if (NV > 0) b[v] = es;
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
       pass2(it, rz[0], rk[0], rt[0], ry[0]);
     }
   }
-  block_sum<8, kThreads>(st8, scratch);
+  block_sum<8, THREADS>(st8, scratch);
 
   const float Bf = (float)p.B, Cf = (float)C;
   const float lse0 = mx[0] + logf(s[0]);
@@ -198,15 +210,15 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
       float g0[VEC], g1[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float sm = (NV > 0 ? a[v] : expf(a[v] - mx[0])) * inv_s0;
+        const float sm = (NV > 0 ? a[v] : fexp(a[v] - mx[0])) * inv_s0;
         if (p.label_kind == 0) g0[v] = (sm * t[0] - d[v]) * wb;
         else g0[v] = (sm - (col + v == label ? 1.f - p.smoothing : 0.f) - p.smoothing / Cf) * wb;
         if (p.kd_kind == 1) {
-          const float ps = (NV > 0 ? b[v] : expf(b[v] * invT - mx[1])) * inv_s1;
-          const float pt = (NV > 0 ? c[v] : expf(c[v] * invT - mx[2])) * inv_s2;
+          const float ps = (NV > 0 ? b[v] : fexp(b[v] * invT - mx[1])) * inv_s1;
+          const float pt = (NV > 0 ? c[v] : fexp(c[v] * invT - mx[2])) * inv_s2;
           g1[v] = (ps - pt) * wk;
         } else if (p.kd_kind == 2) {
-          const float ps = (NV > 0 ? b[v] : expf(b[v] - mx[1])) * inv_s1;
+          const float ps = (NV > 0 ? b[v] : fexp(b[v] - mx[1])) * inv_s1;
           g1[v] = (ps - (col + v == hard_idx ? 1.f : 0.f)) * wk;
         }
       }
@@ -226,24 +238,31 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
     }
   }
 
-  // ---- per-row partials; last CTA folds them in a fixed order ----------------------------------
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     p.row_base[row] = base_row;
     p.row_kd[row] = kd_row;
+  }
+}
+
+// Last CTA to finish folds the per-row partials in a fixed order (bit-reproducible) into {total, base, kd}.
+template <int THREADS = kThreads>
+__device__ __forceinline__ void logit_finalize(const LogitKdParams& p, float* scratch, bool* s_last) {
+  const float Bf = (float)p.B, Cf = (float)p.C;
+  if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int done = atomicAdd(p.ticket, 1u);
-    s_last = (done == (unsigned int)(p.B - 1));
+    *s_last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!*s_last) return;
   __threadfence();
   float acc[2] = {0.f, 0.f};
   // fixed thread->row assignment and fixed tree => bit-reproducible
-  for (int64_t r = threadIdx.x; r < p.B; r += kThreads) {
+  for (int64_t r = threadIdx.x; r < p.B; r += THREADS) {
     acc[0] += __ldcg(p.row_base + r);
     acc[1] += __ldcg(p.row_kd + r);
   }
-  block_sum<2, kThreads>(acc, scratch);
+  block_sum<2, THREADS>(acc, scratch);
   if (threadIdx.x == 0) {
     const float base = acc[0] / Bf;  // 0 when label_kind < 0 (KD term only: total = alpha * kd)
     float kd = 0.f, total = base;
@@ -256,11 +275,67 @@ __global__ void __launch_bounds__(kThreads) logit_kd_kernel(LogitKdParams p) {
   }
 }
 
+// Large batches fold in a second launch: a 1024-thread CTA with 8 independent loads in flight per thread (a 128-thread
+// fold of 16 384 rows is ~130 dependent L2 round trips — it was most of the runtime of the fused form at B = 16 384).
+// Fixed thread -> row assignment and fixed reduction tree: bit-reproducible.
+constexpr int kFoldThreads = 1024;
+__global__ void __launch_bounds__(kFoldThreads) logit_fold_kernel(LogitKdParams p) {
+  __shared__ float scratch[2 * (kFoldThreads / 32)];
+  float a0[8], a1[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a0[u] = a1[u] = 0.f;
+  for (int64_t r0 = threadIdx.x; r0 < p.B; r0 += 8 * kFoldThreads) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t r = r0 + (int64_t)u * kFoldThreads;
+      if (r < p.B) { a0[u] += __ldcg(p.row_base + r); a1[u] += __ldcg(p.row_kd + r); }
+    }
+  }
+  float acc[2] = {((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7])),
+                  ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]))};
+  block_sum<2, kFoldThreads>(acc, scratch);
+  if (threadIdx.x == 0) {
+    const float Bf = (float)p.B, Cf = (float)p.C;
+    const float base = acc[0] / Bf;
+    float kd = 0.f, total = base;
+    if (p.kd_kind == 1) { kd = acc[1] * p.tau * p.tau / (Bf * Cf); total = base * (1.f - p.alpha) + kd * p.alpha; }
+    else if (p.kd_kind == 2) { kd = acc[1] / Bf; total = base * (1.f - p.alpha) + kd * p.alpha; }
+    p.loss_out[0] = total;
+    p.loss_out[1] = base;
+    p.loss_out[2] = kd;
+  }
+}
+
+template <typename T, int VEC, int NV, int THREADS = kThreads, bool TICKET = true>
+__global__ void __launch_bounds__(THREADS) logit_kd_kernel(LogitKdParams p) {
+  __shared__ float scratch[8 * (kThreads / 32)];
+  __shared__ int s_arg[kThreads / 32];
+  __shared__ float s_argv[kThreads / 32];
+  __shared__ bool s_last;
+  const int64_t row = blockIdx.x, C = p.C;
+  const T* z = p.label_kind >= 0 ? reinterpret_cast<const T*>(p.z) + row * C : nullptr;
+  const T* zk = p.kd_kind ? reinterpret_cast<const T*>(p.zk) + row * C : nullptr;
+  const T* zt = p.kd_kind ? reinterpret_cast<const T*>(p.zt) + row * C : nullptr;
+  const T* y = p.label_kind == 0 ? reinterpret_cast<const T*>(p.y) + row * C : nullptr;
+  logit_row<T, VEC, NV, THREADS>(p, row, z, zk, zt, y, scratch, s_arg, s_argv);
+  if (TICKET) logit_finalize<THREADS>(p, scratch, &s_last);
+}
+
 template <typename T, int VEC>
 int launch_logit_kd(const LogitKdParams& p, cudaStream_t stream) {
   const int64_t per_chunk = (int64_t)kThreads * VEC;
   const int64_t nchunk = (p.C + per_chunk - 1) / per_chunk;
   dim3 grid((unsigned)p.B), block(kThreads);
+  const int64_t nchunk64 = (p.C + 64 * VEC - 1) / (64 * VEC);
+  if (p.B >= 1024 && nchunk64 <= 4) {   // large batch: 2-warp CTAs
+    if (nchunk64 <= 1) logit_kd_kernel<T, VEC, 1, 64, false><<<grid, 64, 0, stream>>>(p);
+    else if (nchunk64 <= 2) logit_kd_kernel<T, VEC, 2, 64, false><<<grid, 64, 0, stream>>>(p);
+    else logit_kd_kernel<T, VEC, 4, 64, false><<<grid, 64, 0, stream>>>(p);
+    int rc = check_launch("dkd_logit_kd_fwdbwd");
+    if (rc != DKD_OK) return rc;
+    logit_fold_kernel<<<1, kFoldThreads, 0, stream>>>(p);
+    return check_launch("dkd_logit_kd_fwdbwd: fold");
+  }
   if (nchunk <= 1) logit_kd_kernel<T, VEC, 1><<<grid, block, 0, stream>>>(p);
   else if (nchunk <= 2) logit_kd_kernel<T, VEC, 2><<<grid, block, 0, stream>>>(p);
   else if (nchunk <= 4) logit_kd_kernel<T, VEC, 4><<<grid, block, 0, stream>>>(p);

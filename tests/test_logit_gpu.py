@@ -62,7 +62,8 @@ def _oracle(kind, z, zk, zt, y, alpha, tau, smoothing=0.1):
 @pytest.mark.parametrize("kind", ["soft", "hard"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,C,int_labels", [(1, 1000, False), (7, 100, False), (5, 1001, True), (3, 21843, False),
-                                            (256, 1000, False), (33, 4100, True), (2, 8, False)])
+                                            (256, 1000, False), (33, 4100, True), (2, 8, False),
+                                            (1500, 1000, False), (1100, 2000, True), (1025, 104, False)])   # >= 1024: streaming kernel
 def test_logit_shapes_and_dtypes(kind, dtype, B, C, int_labels):
     from deltakd_b200 import functional as Fn
     from deltakd_b200 import synth
