@@ -474,6 +474,8 @@ class DeiTKDStep(Workload):
         teacher = deit.create_model("deit_small_distilled_patch16_224").to(device).eval()
         for p_ in teacher.parameters():
             p_.requires_grad_(False)
+        if device.type == "cuda":
+            teacher = teacher.to(torch.bfloat16)   # frozen: keep bf16 weights instead of autocast-casting them every step
         student = deit.create_model(self.student_name).to(device)
         H.attach_distillation_heads(student, teacher, args, self.student_name)
         student = student.to(device).train()
@@ -565,7 +567,7 @@ class _Autocast(torch.nn.Module):
 
     def forward(self, x):
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            return self.inner(x)
+            return self.inner(x.to(torch.bfloat16))
 
 
 class DeiTKDStepCurKD(DeiTKDStep):

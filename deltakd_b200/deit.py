@@ -61,7 +61,10 @@ class DeiT(nn.Module):
         self.distilled = distilled
         self.distilled_training = False
         n = (img_size // patch) ** 2
-        self.patch_embed = nn.Conv2d(3, embed_dim, kernel_size=patch, stride=patch)
+        self.patch = patch
+        # non-overlapping 16x16 patches: the stride-16 convolution is a GEMM over unfolded patches (same parameters,
+        # [D, 3*16*16] weight) — cuDNN's strided-conv kernel is ~5x slower than the GEMM at these shapes
+        self.patch_embed = nn.Linear(3 * patch * patch, embed_dim)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim)) if distilled else None
         self.pos_embed = nn.Parameter(torch.randn(1, n + (2 if distilled else 1), embed_dim) * 0.02)
@@ -74,7 +77,10 @@ class DeiT(nn.Module):
         self.distilled_training = enable
 
     def forward(self, x):
-        x = self.patch_embed(x).flatten(2).transpose(1, 2)
+        B, C, H, W = x.shape
+        pz = self.patch
+        x = x.reshape(B, C, H // pz, pz, W // pz, pz).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // pz) * (W // pz), C * pz * pz)
+        x = self.patch_embed(x)
         toks = [self.cls_token.expand(x.shape[0], -1, -1)]
         if self.distilled:
             toks.append(self.dist_token.expand(x.shape[0], -1, -1))
