@@ -11,7 +11,7 @@ __all__ = ["DistillationLoss", "call_base_loss", "random_masking", "saliency_mas
 
 def __getattr__(name):  # lazy: `import deltakd_b200.synth` must work without the CUDA library
     if name in ("DistillationLoss", "call_base_loss", "lrkd_loss", "curkd_loss", "mgd_loss",
-                "saliency_mgd_loss", "vitkd_loss", "SoftTargetCrossEntropy", "LabelSmoothingCrossEntropy"):
+                "saliency_mgd_loss", "vitkd_loss", "diffkd_loss", "SoftTargetCrossEntropy", "LabelSmoothingCrossEntropy"):
         from . import loss
         return getattr(loss, name)
     if name in ("random_masking", "saliency_masking"):

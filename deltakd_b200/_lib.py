@@ -38,6 +38,8 @@ SIGNATURES = {
     "dkd_align_mse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_masked_generation_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_masked_generation_fwdbwd": (_i, [_p] * 10 + [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _f] + [_p] * 10 + [_sz, _p]),
+    "dkd_align_nmse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
+    "dkd_align_nmse_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "dkd_wass_l1_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_wass_l1_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "dkd_wass_sinkhorn_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),

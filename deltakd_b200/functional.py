@@ -247,6 +247,15 @@ def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 
     return _AlignMseLayers.apply(_entry, scale, n, s_off, t_off, *s_list, *t_list, *w_list, *b_list)
 
 
+def align_normalized_mse_loss(s_feats, t_feats, linears, s_off: int = 1, t_off: int = 2):
+    """sum_i mean((normalize(linears[i](s_i[:, s_off:])) - normalize(t_i[:, t_off:]))**2), L2-normalised per token over the
+    channel axis (diffkd branch, loss.py:139-140,149).  0-dim fp32; weight it with ordinary tensor arithmetic (the
+    DiffKD weight w_t.mean() is a device scalar) — backward rescales the stored gradients on the device."""
+    B, Ts, _ = s_feats[0].shape
+    numel = B * (Ts - s_off) * t_feats[0].shape[-1]
+    return align_mse_layers_loss(s_feats, t_feats, linears, 1.0 / numel, s_off, t_off, _entry="dkd_align_nmse")
+
+
 def wass_l1_loss(s_feats, t_feats, linears, weight: float = 5.0, s_off: int = 1, t_off: int = 2):
     """weight * mean_i mean|sort_tokens(linears[i](s_i[:, s_off:])) - sort_tokens(t_i[:, t_off:])| (loss.py:187-199,226).
     `weight` (the reference's x5) is folded into the kernels so backward needs no rescale pass."""

@@ -47,6 +47,19 @@ class SimpleCrossAttention(nn.Module):
                                        self.k.weight, self.k.bias, self.num_heads)
 
 
+class DenoisingNetwork(nn.Module):
+    """DiffKD noise predictor (reference models.py:103-121; same sub-module names -> same state_dict keys)."""
+
+    def __init__(self, dims: int):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dims, dims * 2), nn.GELU(), nn.Linear(dims * 2, dims), nn.Dropout(0.1))
+        self.time_embed = nn.Sequential(nn.Linear(1, dims), nn.GELU(), nn.Linear(dims, dims))
+
+    def forward(self, x, t):
+        t_emb = self.time_embed(t.float().view(-1, 1))
+        return self.net(x + t_emb.unsqueeze(1))
+
+
 def _generation(dim: int) -> nn.Sequential:
     return nn.Sequential(
         nn.Conv2d(dim, dim, kernel_size=3, padding=1),
@@ -74,6 +87,9 @@ def attach_distillation_heads(student_model: nn.Module, teacher_model: nn.Module
         student_model.align = _linears(3, ds, args.lrkd_rank)
     elif "deit" in student_model_name and kind in ("soft", "hard"):
         student_model.set_distilled_training(enable=True)
+    elif kind == "diffkd":
+        student_model.denoise_fn = DenoisingNetwork(dt)
+        student_model.align = _linears(3, ds, dt)
     elif kind == "saliency_mgd":
         student_model.align = nn.Linear(ds, dt, bias=True)
         student_model.mask_token = nn.Parameter(torch.zeros(1, 1, dt))

@@ -21,7 +21,7 @@ from . import functional as Fn
 from .features import forward_with_features, unwrap
 from .misc import len_keep_of, saliency_scores
 
-_FEATURE_TYPES = ("vitkd", "lrkd", "curkd", "saliency_mgd", "wasskd", "mgd")
+_FEATURE_TYPES = ("vitkd", "lrkd", "diffkd", "curkd", "saliency_mgd", "wasskd", "mgd")
 
 
 class SoftTargetCrossEntropy(nn.Module):
@@ -116,6 +116,8 @@ class DistillationLoss(nn.Module):
             kd_a = Fn.lrkd_layers_loss(s_sel, t_sel, list(student.align), args.lrkd_rank,
                                        (args.lrkd_alpha, args.lrkd_beta, args.lrkd_gamma), weight=self.alpha)
             return base_loss * (1 - self.alpha) + kd_a
+        if kind == 'diffkd':
+            return base_loss * (1 - self.alpha) + diffkd_loss(student, student_features, teacher_features) * self.alpha
         if kind == 'curkd':
             return base_loss + curkd_loss(student, student_features, teacher_features, args)
         if kind == 'saliency_mgd':
@@ -147,6 +149,32 @@ def vitkd_loss(student_model, student_features, teacher_features,
                                     student_model.mask_token, student_model.generation,
                                     mask_ratio=lambda_vitkd, scale=beta_vitkd / lambda_vitkd / B)
     return lr + gen
+
+
+def diffkd_loss(student_model, student_features, teacher_features, T: int = 8, lambda_feat: float = 5e-5):
+    """diffkd branch (loss.py:105-155), layers (0, 1, -1).  The RNG draws (diffusion step per sample, noise per
+    layer) stay torch calls in the reference's order; the noise predictor `student_model.denoise_fn` is a module call
+    as in the reference (an MLP head with Dropout); the feature term — alignment Linear, per-token L2 normalisation
+    of student and teacher, MSE, and all its gradients — is one fused native call for the three layers."""
+    import math
+    import torch.nn.functional as F
+    s_sel = [student_features[0], student_features[1], student_features[-1]]
+    t_sel = [teacher_features[0], teacher_features[1], teacher_features[-1]]
+    dev = s_sel[0].device
+    B = s_sel[0].shape[0]
+    t = torch.randint(0, T, (B,), device=dev)
+    sigma_max = torch.where(t < T // 2, torch.tensor(0.3, device=dev), torch.tensor(0.7, device=dev))
+    sigma_t = (1 - torch.cos(math.pi * t.float() / T)) * sigma_max
+    noise_loss = 0
+    with torch.no_grad():
+        t_hat = [F.normalize(tf[:, 2:].float(), p=2, dim=-1, eps=0.0) for tf in t_sel]
+    for th in t_hat:
+        noise = torch.randn_like(th) * sigma_t.view(-1, 1, 1)
+        pred_noise = student_model.denoise_fn(th + noise, t)
+        noise_loss = noise_loss + F.mse_loss(pred_noise.float(), noise)
+    w_t = 1 / (sigma_t ** 2 + 1e-8)
+    feat = Fn.align_normalized_mse_loss(s_sel, t_sel, list(student_model.align))
+    return (noise_loss + w_t.mean() * feat) / len(s_sel) * lambda_feat
 
 
 def lrkd_loss(teacher_features, student_features, rank=10, alpha=0.1, beta=0.1, gamma=0.1):

@@ -127,6 +127,22 @@ DKD_API int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, c
                                  size_t workspace_bytes, dkd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Normalised hidden-state matching (feature term of DiffKD), forward + backward:
+ *     a = s[:, s_off:, :] W^T + bias ;  a_hat = a/|a|, t_hat = t[:, t_off:, :]/|t| (L2 over channels, per token)
+ *     *loss += scale * sum (a_hat - t_hat)^2     (accumulates);  g_s, g_W, g_b as in dkd_align_mse_fwdbwd
+ * Replaces, per layer of the diffkd branch (model/loss.py:112-116, 139-140, 149), the alignment Linear, the two
+ * per-token L2 normalisations and `F.mse_loss(s_feat, t_feat)` with their backward; the caller folds 1/numel into
+ * `scale` and applies the data-dependent weight w_t.mean() (a device scalar) through the autograd rescale.
+ * Same argument conventions as dkd_align_mse_fwdbwd.  The noise-prediction term of that branch
+ * (`student.denoise_fn`, an nn.Module with Dropout) stays a module call.
+ */
+DKD_API size_t dkd_align_nmse_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
+DKD_API int dkd_align_nmse_fwdbwd(const void* s, const void* t, const float* W, const float* bias, int64_t B, int Ts,
+                                  int s_off, int Tt, int t_off, int n_tok, int Ds, int Dt, int dtype, int precision,
+                                  float scale, void* g_s, float* g_W, float* g_b, float* loss, void* workspace,
+                                  size_t workspace_bytes, dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * WassKD 'l1' term of one layer, forward + backward:
  *     a = s[:, s_off:, :] W^T + bias ;  per (sample, channel): sort the n_tok values of a and of t[:, t_off:, :]
  *     *loss += scale * sum |sort(a) - sort(t)|                (accumulates)

@@ -262,10 +262,43 @@ def wass_sinkhorn(s_feats, t_feats, heads, blur: float = 0.05) -> torch.Tensor:
     return total / 3.0
 
 
+def denoise_fn(x: torch.Tensor, t: torch.Tensor, heads: dict) -> torch.Tensor:
+    """student.denoise_fn = DenoisingNetwork(Dt) (models.py:103-121): time embedding Linear(1,D)-GELU-Linear(D,D)
+    added to every token, then Linear(D,2D)-GELU-Linear(2D,D)-Dropout(0.1).  Dropout is evaluated in eval mode
+    (identity): its mask is a torch RNG draw, outside what parity can pin."""
+    te = F.linear(t.to(x.dtype).view(-1, 1), heads["denoise_fn.time_embed.0.weight"], heads["denoise_fn.time_embed.0.bias"])
+    te = F.linear(F.gelu(te), heads["denoise_fn.time_embed.2.weight"], heads["denoise_fn.time_embed.2.bias"])
+    h = F.linear(x + te.unsqueeze(1), heads["denoise_fn.net.0.weight"], heads["denoise_fn.net.0.bias"])
+    return F.linear(F.gelu(h), heads["denoise_fn.net.2.weight"], heads["denoise_fn.net.2.bias"])
+
+
+def diffkd(s_feats, t_feats, heads, t: torch.Tensor, noises, T: int = 8) -> torch.Tensor:
+    """diffkd branch (loss.py:105-155): layers (0, 1, -1); L2-normalised tokens; noise = randn * sigma_t with
+    sigma_t = (1 - cos(pi t / T)) * (0.3 if t < T/2 else 0.7); per layer mse(denoise_fn(t_hat + noise, t), noise)
+    + mean_b(1 / (sigma_t^2 + 1e-8)) * mse(s_hat, t_hat); mean of the 3 layers, times lambda_feat = 5e-5.
+    `t` (int [B], the reference's torch.randint draw) and `noises` (3 x randn_like draws, BEFORE the sigma scaling)
+    are inputs so that parity does not depend on RNG streams."""
+    dt = t_feats[0].dtype
+    sigma_max = torch.where(t < T // 2, torch.tensor(0.3), torch.tensor(0.7))
+    sigma_t = ((1 - torch.cos(math.pi * t.float() / T)) * sigma_max)
+    total = 0.0
+    for j, (si, ti) in enumerate(((0, 0), (1, 1), (-1, -1))):
+        a = _align(s_feats[si], heads[f"align.{j}.weight"], heads[f"align.{j}.bias"])
+        tf = t_feats[ti][:, 2:]
+        tn = tf / torch.norm(tf, p=2, dim=-1, keepdim=True)
+        sn = a / torch.norm(a, p=2, dim=-1, keepdim=True)
+        noise = noises[j].to(dt) * sigma_t.view(-1, 1, 1)      # fp32 sigma promotes as in the reference
+        pred = denoise_fn(tn + noise, t, heads)
+        total = total + F.mse_loss(pred, noise.to(pred.dtype))
+        w_t = 1 / (sigma_t ** 2 + 1e-8)
+        total = total + w_t.mean() * F.mse_loss(sn, tn)
+    return total / 3 * 5e-5
+
+
 # --------------------------------------------------------------------------- dispatcher
 def distillation_loss(dtype_: str, outputs, labels, teacher_logits, s_feats, t_feats, heads, args,
                       alpha: float, tau: float, base_kind: str = "soft_target", noise=None,
-                      lrkd_signs=None, probe=None) -> torch.Tensor:
+                      lrkd_signs=None, probe=None, diff_t=None, diff_noises=None) -> torch.Tensor:
     """DistillationLoss.forward (loss.py:29-242) with the teacher outputs passed in."""
     outputs_kd = None
     if not isinstance(outputs, torch.Tensor):
@@ -285,6 +318,8 @@ def distillation_loss(dtype_: str, outputs, labels, teacher_logits, s_feats, t_f
     elif t == "lrkd":
         kd = lrkd(s_feats, t_feats, heads, args.lrkd_rank,
                   (args.lrkd_alpha, args.lrkd_beta, args.lrkd_gamma), lrkd_signs)
+    elif t == "diffkd":
+        kd = diffkd(s_feats, t_feats, heads, diff_t, diff_noises)
     elif t == "curkd":
         if args.current_epoch < 151:
             return base + curkd_hidden(s_feats, t_feats, heads, args.current_epoch)

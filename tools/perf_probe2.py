@@ -59,6 +59,13 @@ elif which == "curkd":
     def f():
         l = Fn.align_mse_layers_loss(s, t, lins, 1e-6); l.backward()
     prof("curkd early, 3 layers", f)
+elif which == "curkd_bf16":
+    s = [mk(B, 197, 192).bfloat16().requires_grad_(True) for _ in range(3)]
+    t = [mk(B, 198, 384).bfloat16() for _ in range(3)]
+    lins = [torch.nn.Linear(192, 384).cuda() for _ in range(3)]
+    def f():
+        l = Fn.align_mse_layers_loss(s, t, lins, 1e-6); l.backward()
+    prof("curkd early bf16, 3 layers", f)
 elif which == "salmgd":
     from deltakd_b200.misc import saliency_scores
     for m in (1, 2, 3):
