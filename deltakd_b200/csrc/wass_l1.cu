@@ -24,6 +24,7 @@ constexpr int kCh = 16;             // channels (columns) per CTA
 constexpr int kMaxTok = 256;        // bitonic width
 constexpr int kPerLane = 32;        // keys per lane: a column is held by 8 adjacent lanes
 constexpr int kQuad = kMaxTok / kPerLane;   // 8 lanes per column
+constexpr int kSearchIlp = 4;
 
 // Keys-only bitonic sort of 256 floats held by 8 adjacent lanes (sorted position e = sub*32 + r, sub = lane & 7).
 // Strides below 32 are in-register compare-exchanges (two FMNMX, 30 stages); strides 32/64/128 (6 stages) cross
@@ -165,14 +166,14 @@ __global__ void __launch_bounds__(kSortThreads) wass_sort_kernel(SortParams p) {
 
   if (p.write_grad) {
     // sign of (student value - its teacher partner), two bit masks per lane (token q*8 + sub -> bit q);
-    // 4 independent searches in flight
+    // 4 independent searches in flight (each is a chain of 8 dependent shared-memory loads; 8 in flight measured slower)
     unsigned pos = 0u, neg = 0u;
 #pragma unroll 1
-    for (int q0 = 0; q0 * kQuad + sub < n_tok; q0 += 4) {
-      float v[4];
-      int r[4];
+    for (int q0 = 0; q0 * kQuad + sub < n_tok; q0 += kSearchIlp) {
+      float v[kSearchIlp];
+      int r[kSearchIlp];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kSearchIlp; ++u) {
         const int tok = (q0 + u) * kQuad + sub;
         v[u] = tok < n_tok ? ca[tok] : INFINITY;
         r[u] = 0;
@@ -180,10 +181,10 @@ __global__ void __launch_bounds__(kSortThreads) wass_sort_kernel(SortParams p) {
 #pragma unroll
       for (int step = 128; step > 0; step >>= 1) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) r[u] += cs[r[u] + step - 1] < v[u] ? step : 0;
+        for (int u = 0; u < kSearchIlp; ++u) r[u] += cs[r[u] + step - 1] < v[u] ? step : 0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kSearchIlp; ++u) {
         const int tok = (q0 + u) * kQuad + sub;
         if (tok < n_tok) {
           int rk = r[u];
