@@ -27,7 +27,7 @@ constexpr int kTok = 196;                   // points per cloud (14 x 14 patch t
 constexpr int kD = 384;                     // teacher width
 constexpr int kLD = 204;                    // allocation pitch of a cost matrix in floats (and the pitch of C_xy)
 constexpr int kLDxy = 204;                  // C_xy: one thread per row -> 8 consecutive rows hit 8 distinct 16-byte bank groups
-constexpr int kLDsym = 200;                 // C_xx, C_yy: two threads per row -> (row, half) pairs hit distinct bank groups
+constexpr int kLDsym = 196;                 // C_xx, C_yy: two threads per row (float4 chunks [0,28) | [28,49)): 4i + 16h distinct bank groups
 constexpr int kCostBytes = kTok * kLD * 4;  // 159 936 (copied whole; the symmetric matrices use the first 196*200 floats)
 constexpr int kLDP = 208;                   // plan row pitch in bf16 (416 B)
 constexpr int kMaxEps = 64;
@@ -205,39 +205,34 @@ __device__ __forceinline__ void load_cost(float* sC, const float* gC, uint64_t* 
 // running maximum m and the sum s = sum 2^(v - m) are rescaled when a chunk raises the maximum (one extra ex2 per
 // chunk) — each cost entry is read from shared memory once per eps step instead of twice.
 struct Lse { float m, s; };
-__device__ __forceinline__ void lse_push(Lse& a, const float (&v)[28], int cnt) {
-  float cm = -INFINITY;
+__device__ __forceinline__ void lse_push(Lse& a, const float (&v)[28]) {
+  float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
 #pragma unroll
-  for (int q = 0; q < 28; ++q) if (q < cnt) cm = fmaxf(cm, v[q]);
-  const float mn = fmaxf(a.m, cm);
+  for (int q = 8; q < 28; q += 4) { c0 = fmaxf(c0, v[q]); c1 = fmaxf(c1, v[q + 1]); c2 = fmaxf(c2, v[q + 2]); c3 = fmaxf(c3, v[q + 3]); }
+  const float mn = fmaxf(a.m, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
   float s0 = a.s * ex2f(a.m - mn), s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int q = 0; q < 28; q += 4) {
-    if (q + 0 < cnt) s0 += ex2f(v[q + 0] - mn);
-    if (q + 1 < cnt) s1 += ex2f(v[q + 1] - mn);
-    if (q + 2 < cnt) s2 += ex2f(v[q + 2] - mn);
-    if (q + 3 < cnt) s3 += ex2f(v[q + 3] - mn);
+    s0 += ex2f(v[q + 0] - mn); s1 += ex2f(v[q + 1] - mn);
+    s2 += ex2f(v[q + 2] - mn); s3 += ex2f(v[q + 3] - mn);
   }
   a.m = mn; a.s = (s0 + s1) + (s2 + s3);
 }
-// float4 chunks [k0, k1) of one row
+// float4 chunks [k0, k1) of one row; k1 - k0 is a multiple of 7 (a row is 49 = 7 x 7 chunks)
 __device__ __forceinline__ Lse lse2_row_part(const float* __restrict__ crow, const float* __restrict__ h, float c2, int k0, int k1) {
   const float4* c4 = reinterpret_cast<const float4*>(crow);
   const float4* h4 = reinterpret_cast<const float4*>(h);
   Lse a{-INFINITY, 0.f};
 #pragma unroll 1
   for (int kb = k0; kb < k1; kb += 7) {
-    const int n4 = min(7, k1 - kb);
     float v[28];
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
-      if (q < n4) {
-        const float4 c = c4[kb + q], hh = h4[kb + q];
-        v[4 * q] = fmaf(-c.x, c2, hh.x); v[4 * q + 1] = fmaf(-c.y, c2, hh.y);
-        v[4 * q + 2] = fmaf(-c.z, c2, hh.z); v[4 * q + 3] = fmaf(-c.w, c2, hh.w);
-      }
+      const float4 c = c4[kb + q], hh = h4[kb + q];
+      v[4 * q] = fmaf(-c.x, c2, hh.x); v[4 * q + 1] = fmaf(-c.y, c2, hh.y);
+      v[4 * q + 2] = fmaf(-c.z, c2, hh.z); v[4 * q + 3] = fmaf(-c.w, c2, hh.w);
     }
-    lse_push(a, v, 4 * n4);
+    lse_push(a, v);
   }
   return a;
 }
@@ -249,7 +244,7 @@ __device__ __forceinline__ Lse lse2_col(const float* __restrict__ ccol, const fl
     float v[28];
 #pragma unroll
     for (int q = 0; q < 28; ++q) v[q] = fmaf(-ccol[(i0 + q) * kLDxy], c2, h[i0 + q]);
-    lse_push(a, v, 28);
+    lse_push(a, v);
   }
   return a;
 }
@@ -305,7 +300,7 @@ __global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kSymThreads, 1) sinkho
   const bool is_col = XY && threadIdx.x >= kRoleThreads;
   const int idx = XY ? (is_col ? threadIdx.x - kRoleThreads : threadIdx.x) : threadIdx.x >> 1;   // row i or column j
   const int half = XY ? 0 : threadIdx.x & 1;
-  const int k0 = XY ? 0 : (half ? 25 : 0), k1 = XY ? K4 : (half ? K4 : 25);   // this thread's float4 chunks of its row
+  const int k0 = XY ? 0 : (half ? 28 : 0), k1 = XY ? K4 : (half ? K4 : 28);   // this thread's float4 chunks of its row (4 | 3 groups of 7)
   const bool active = idx < kTok;
   const float logw = -__logf((float)kTok);
   float pot = 0.f;            // f_ba[i] / g_ab[j] (xy) or f_aa[i] / g_bb[i] (sym; both halves hold the same value)
