@@ -43,13 +43,18 @@ struct LogitKdParams {
 // One batch row: block-reduced maxima / sums, both gradient rows written, per-row loss partials stored.
 // z / zk / zt / y point at the row's operands — in global memory (one CTA per row) or in a shared-memory stage
 // filled by bulk copies (streaming kernel below); the arithmetic is the same code.
-template <typename T, int VEC, int NV, int THREADS = kThreads>
+// LK / KK: label_kind / kd_kind as compile-time constants (kRuntimeMode = read them from the parameters).  The common
+// modes are instantiated so that the per-element mode tests vanish from the unrolled inner loops.
+constexpr int kRuntimeMode = -2;
+template <typename T, int VEC, int NV, int THREADS = kThreads, int LK = kRuntimeMode, int KK = kRuntimeMode>
 __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, const T* z, const T* zk, const T* zt, const T* y,
                                           float* scratch, int* s_arg, float* s_argv) {
   const int64_t C = p.C;
+  const int label_kind = LK == kRuntimeMode ? p.label_kind : LK;
+  const int kd_kind = KK == kRuntimeMode ? p.kd_kind : KK;
   const int tid = THREADS == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;   // THREADS == 32: one warp per row
-  const int64_t label = p.label_kind == 1 ? reinterpret_cast<const int64_t*>(p.y)[row] : -1;
-  const float invT = p.kd_kind == 1 ? 1.f / p.tau : 1.f;
+  const int64_t label = label_kind == 1 ? reinterpret_cast<const int64_t*>(p.y)[row] : -1;
+  const float invT = kd_kind == 1 ? 1.f / p.tau : 1.f;
 
   constexpr int NVR = NV > 0 ? NV : 1;
   float rz[NVR][VEC], rk[NVR][VEC], rt[NVR][VEC], ry[NVR][VEC];
@@ -60,11 +65,11 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   // col < C themselves), and operands a mode does not use alias one it does (their values are never read; the
   // duplicate loads hit L1).  Kernel-uniform branches on the mode split the loads into basic blocks, each exposing
   // its own DRAM round trip (ncu: six equal long-scoreboard stalls per row); this way they issue back to back.
-  const T* any = p.label_kind >= 0 ? z : zk;
-  const T* lz = p.label_kind >= 0 ? z : any;
-  const T* lzk = p.kd_kind ? zk : any;
-  const T* lzt = p.kd_kind ? zt : any;
-  const T* ly = p.label_kind == 0 ? y : any;
+  const T* any = label_kind >= 0 ? z : zk;
+  const T* lz = label_kind >= 0 ? z : any;
+  const T* lzk = kd_kind ? zk : any;
+  const T* lzt = kd_kind ? zt : any;
+  const T* ly = label_kind == 0 ? y : any;
   auto load4 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
     const int64_t col0 = col_of(it);
     const int64_t col = col0 < C ? col0 : 0;  // C % VEC == 0 by construction
@@ -72,7 +77,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
     Vec<T, VEC>::load(lzk + col, b);
     Vec<T, VEC>::load(lzt + col, c);
     Vec<T, VEC>::load(ly + col, d);
-    if (p.label_kind < 0) {
+    if (label_kind < 0) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) a[v] = 0.f;
     }
@@ -88,10 +93,10 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         mx[0] = fmaxf(mx[0], a[v]);
-        if (p.kd_kind) {
+        if (kd_kind) {
           mx[1] = fmaxf(mx[1], b[v] * invT);
           mx[2] = fmaxf(mx[2], c[v] * invT);
-          if (p.kd_kind == 2 && c[v] > best) { best = c[v]; best_i = col + v; }  // first max within thread
+          if (kd_kind == 2 && c[v] > best) { best = c[v]; best_i = col + v; }  // first max within thread
         }
       }
     }
@@ -113,7 +118,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   block_max<3, THREADS>(mx, scratch);
   int64_t tgt = label;  // index whose one-hot enters the KD gradient (hard) -- label handled separately
   int64_t hard_idx = -1;
-  if (p.kd_kind == 2) {
+  if (kd_kind == 2) {
     // argmax with first-index tie-break: warp shuffle, then across warps
     float bv = best;
     long long bi = (long long)best_i;
@@ -152,17 +157,17 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
       for (int v = 0; v < VEC; ++v) {
         const float ea = fexp(a[v] - mx[0]);
         s[0] += ea;
-        if (p.label_kind == 0) { t[0] += d[v]; t[1] += d[v] * a[v]; }
+        if (label_kind == 0) { t[0] += d[v]; t[1] += d[v] * a[v]; }
         else { t[1] += a[v]; if (col + v == label) t[2] = a[v]; }
         if (NV > 0) a[v] = ea;
-        if (p.kd_kind == 1) {
+        if (kd_kind == 1) {
           const float av = b[v] * invT, bv = c[v] * invT;
           const float eb = fexp(bv - mx[2]), es = fexp(av - mx[1]);
           s[1] += es;
           s[2] += eb;
           s[3] += eb * (bv - av);
           if (NV > 0) { b[v] = es; c[v] = eb; }
-        } else if (p.kd_kind == 2) {
+        } else if (kd_kind == 2) {
           const float es = fexp(b[v] - mx[1]);
           s[1] += es;
           if (col + v == hard_idx) t[3] = b[v];
@@ -185,25 +190,25 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   const float Bf = (float)p.B, Cf = (float)C;
   const float lse0 = mx[0] + logf(s[0]);
   float base_row, kd_row = 0.f;
-  if (p.label_kind < 0) base_row = 0.f;
-  else if (p.label_kind == 0) base_row = lse0 * t[0] - t[1];
+  if (label_kind < 0) base_row = 0.f;
+  else if (label_kind == 0) base_row = lse0 * t[0] - t[1];
   else base_row = (1.f - p.smoothing) * (lse0 - t[2]) + p.smoothing * (lse0 - t[1] / Cf);
   float lse1 = 0.f, lse2 = 0.f;
-  if (p.kd_kind == 1) {
+  if (kd_kind == 1) {
     lse1 = mx[1] + logf(s[1]);
     lse2 = mx[2] + logf(s[2]);
     kd_row = s[3] / s[2] - lse2 + lse1;  // sum_c p_t (log p_t - log p_s)
-  } else if (p.kd_kind == 2) {
+  } else if (kd_kind == 2) {
     lse1 = mx[1] + logf(s[1]);
     kd_row = lse1 - t[3];
   }
 
   // ---- pass 3: gradients -----------------------------------------------------------------------
-  const float wb = (p.kd_kind == 0 ? 1.f : 1.f - p.alpha) / Bf;           // d total / d base_row
-  const float wk = p.kd_kind == 1 ? p.alpha * p.tau / (Bf * Cf) : p.alpha / Bf;
-  const float inv_s0 = 1.f / s[0], inv_s1 = p.kd_kind ? 1.f / s[1] : 0.f, inv_s2 = p.kd_kind == 1 ? 1.f / s[2] : 0.f;
-  T* gz = (p.gz && p.label_kind >= 0) ? reinterpret_cast<T*>(p.gz) + row * C : nullptr;
-  T* gzk = (p.gzk && p.kd_kind) ? reinterpret_cast<T*>(p.gzk) + row * C : nullptr;
+  const float wb = (kd_kind == 0 ? 1.f : 1.f - p.alpha) / Bf;           // d total / d base_row
+  const float wk = kd_kind == 1 ? p.alpha * p.tau / (Bf * Cf) : p.alpha / Bf;
+  const float inv_s0 = 1.f / s[0], inv_s1 = kd_kind ? 1.f / s[1] : 0.f, inv_s2 = kd_kind == 1 ? 1.f / s[2] : 0.f;
+  T* gz = (p.gz && label_kind >= 0) ? reinterpret_cast<T*>(p.gz) + row * C : nullptr;
+  T* gzk = (p.gzk && kd_kind) ? reinterpret_cast<T*>(p.gzk) + row * C : nullptr;
   auto pass3 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
     const int64_t col = col_of(it);
     if (col < C) {
@@ -211,13 +216,13 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float sm = (NV > 0 ? a[v] : fexp(a[v] - mx[0])) * inv_s0;
-        if (p.label_kind == 0) g0[v] = (sm * t[0] - d[v]) * wb;
+        if (label_kind == 0) g0[v] = (sm * t[0] - d[v]) * wb;
         else g0[v] = (sm - (col + v == label ? 1.f - p.smoothing : 0.f) - p.smoothing / Cf) * wb;
-        if (p.kd_kind == 1) {
+        if (kd_kind == 1) {
           const float ps = (NV > 0 ? b[v] : fexp(b[v] * invT - mx[1])) * inv_s1;
           const float pt = (NV > 0 ? c[v] : fexp(c[v] * invT - mx[2])) * inv_s2;
           g1[v] = (ps - pt) * wk;
-        } else if (p.kd_kind == 2) {
+        } else if (kd_kind == 2) {
           const float ps = (NV > 0 ? b[v] : fexp(b[v] - mx[1])) * inv_s1;
           g1[v] = (ps - (col + v == hard_idx ? 1.f : 0.f)) * wk;
         }
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(kFoldThreads) logit_fold_kernel(LogitKdParams 
   }
 }
 
-template <typename T, int VEC, int NV, int THREADS = kThreads, bool TICKET = true>
+template <typename T, int VEC, int NV, int THREADS = kThreads, bool TICKET = true, int LK = kRuntimeMode, int KK = kRuntimeMode>
 __global__ void __launch_bounds__(THREADS) logit_kd_kernel(LogitKdParams p) {
   __shared__ float scratch[8 * (kThreads / 32)];
   __shared__ int s_arg[kThreads / 32];
@@ -317,8 +322,29 @@ __global__ void __launch_bounds__(THREADS) logit_kd_kernel(LogitKdParams p) {
   const T* zk = p.kd_kind ? reinterpret_cast<const T*>(p.zk) + row * C : nullptr;
   const T* zt = p.kd_kind ? reinterpret_cast<const T*>(p.zt) + row * C : nullptr;
   const T* y = p.label_kind == 0 ? reinterpret_cast<const T*>(p.y) + row * C : nullptr;
-  logit_row<T, VEC, NV, THREADS>(p, row, z, zk, zt, y, scratch, s_arg, s_argv);
+  logit_row<T, VEC, NV, THREADS, LK, KK>(p, row, z, zk, zt, y, scratch, s_arg, s_argv);
   if (TICKET) logit_finalize<THREADS>(p, scratch, &s_last);
+}
+
+// one (threads, ticket) shape; NV by row length; the six usual (label_kind, kd_kind) modes are compiled in
+template <typename T, int VEC, int THREADS, bool TICKET, int LK, int KK>
+void launch_nv(const LogitKdParams& p, int64_t nchunk, dim3 grid, cudaStream_t stream) {
+  if (nchunk <= 1) logit_kd_kernel<T, VEC, 1, THREADS, TICKET, LK, KK><<<grid, THREADS, 0, stream>>>(p);
+  else if (nchunk <= 2) logit_kd_kernel<T, VEC, 2, THREADS, TICKET, LK, KK><<<grid, THREADS, 0, stream>>>(p);
+  else logit_kd_kernel<T, VEC, 4, THREADS, TICKET, LK, KK><<<grid, THREADS, 0, stream>>>(p);
+}
+template <typename T, int VEC, int THREADS, bool TICKET>
+void launch_mode(const LogitKdParams& p, int64_t nchunk, dim3 grid, cudaStream_t stream) {
+  if constexpr (VEC * sizeof(T) == 16) {   // specialise the vectorised kernels only
+    const int lk = p.label_kind, kk = p.kd_kind;
+    if (lk == 0 && kk == 1) return launch_nv<T, VEC, THREADS, TICKET, 0, 1>(p, nchunk, grid, stream);
+    if (lk == 1 && kk == 1) return launch_nv<T, VEC, THREADS, TICKET, 1, 1>(p, nchunk, grid, stream);
+    if (lk == 0 && kk == 2) return launch_nv<T, VEC, THREADS, TICKET, 0, 2>(p, nchunk, grid, stream);
+    if (lk == 1 && kk == 2) return launch_nv<T, VEC, THREADS, TICKET, 1, 2>(p, nchunk, grid, stream);
+    if (lk == 0 && kk == 0) return launch_nv<T, VEC, THREADS, TICKET, 0, 0>(p, nchunk, grid, stream);
+    if (lk == 1 && kk == 0) return launch_nv<T, VEC, THREADS, TICKET, 1, 0>(p, nchunk, grid, stream);
+  }
+  launch_nv<T, VEC, THREADS, TICKET, kRuntimeMode, kRuntimeMode>(p, nchunk, grid, stream);
 }
 
 template <typename T, int VEC>
@@ -327,18 +353,14 @@ int launch_logit_kd(const LogitKdParams& p, cudaStream_t stream) {
   const int64_t nchunk = (p.C + per_chunk - 1) / per_chunk;
   dim3 grid((unsigned)p.B), block(kThreads);
   const int64_t nchunk64 = (p.C + 64 * VEC - 1) / (64 * VEC);
-  if (p.B >= 1024 && nchunk64 <= 4) {   // large batch: 2-warp CTAs
-    if (nchunk64 <= 1) logit_kd_kernel<T, VEC, 1, 64, false><<<grid, 64, 0, stream>>>(p);
-    else if (nchunk64 <= 2) logit_kd_kernel<T, VEC, 2, 64, false><<<grid, 64, 0, stream>>>(p);
-    else logit_kd_kernel<T, VEC, 4, 64, false><<<grid, 64, 0, stream>>>(p);
+  if (p.B >= 1024 && nchunk64 <= 4) {   // large batch: 2-warp CTAs, fold in a second launch
+    launch_mode<T, VEC, 64, false>(p, nchunk64, grid, stream);
     int rc = check_launch("dkd_logit_kd_fwdbwd");
     if (rc != DKD_OK) return rc;
     logit_fold_kernel<<<1, kFoldThreads, 0, stream>>>(p);
     return check_launch("dkd_logit_kd_fwdbwd: fold");
   }
-  if (nchunk <= 1) logit_kd_kernel<T, VEC, 1><<<grid, block, 0, stream>>>(p);
-  else if (nchunk <= 2) logit_kd_kernel<T, VEC, 2><<<grid, block, 0, stream>>>(p);
-  else if (nchunk <= 4) logit_kd_kernel<T, VEC, 4><<<grid, block, 0, stream>>>(p);
+  if (nchunk <= 4) launch_mode<T, VEC, kThreads, true>(p, nchunk, grid, stream);
   else logit_kd_kernel<T, VEC, 0><<<grid, block, 0, stream>>>(p);
   return check_launch("dkd_logit_kd_fwdbwd");
 }
