@@ -82,7 +82,8 @@ struct ConvEpi {
   struct State { float acc; };
   static __device__ __forceinline__ void init(const Params&, State& st) { st.acc = 0.f; }
 
-  static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc) {
+  static __device__ __forceinline__ void tile(const Params& p, State& st, int m0, int n0, int row_in_tile, uint32_t t_acc, int group = 0,
+                                              int groups = 1) {
     const int64_t m = (int64_t)m0 + row_in_tile;
     const bool live = row_in_tile < Cfg::TILE_M && m < p.M;
     float mk = 0.f;
@@ -93,7 +94,7 @@ struct ConvEpi {
       trow = b * p.Tt + p.t_off + (m - b * p.n_tok);
     }
 #pragma unroll 1
-    for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
+    for (int c0 = group * 32; c0 < Cfg::BN; c0 += 32 * groups) {
       float v[32];
       sm100::tmem_ld32(t_acc + c0, v);
       float aux[32];
@@ -128,7 +129,7 @@ struct ConvEpi {
   }
 
   static __device__ __forceinline__ void finish(const Params& p, State& st, int tid) {
-    if (MODE == EPI_MSE) epilogue_block_partial(st.acc, tid, p.partials);
+    if (MODE == EPI_MSE) epilogue_block_partial<Cfg::EPI_WARPS>(st.acc, tid, p.partials);
   }
 };
 

@@ -20,9 +20,9 @@
 namespace dkd {
 namespace {
 
-using AlignCfg = GemmCfg<192, 1, 4, 2>;              // X tile 128 x 192 (K = 192)
-using ConvCfg = GemmCfg<384, 2, 3, 1, 126>;          // 9 image rows x 384 channels, K = 9 x 384
-using DalignCfg = GemmCfg<192, 1, 4, 2>;             // g_s tile 128 x 192 (K = 384)
+using AlignCfg = GemmCfg<192, 1, 4, 2, 128, 1, 8>;   // X tile 128 x 192 (K = 192), 8 epilogue warps
+using ConvCfg = GemmCfg<384, 2, 3, 1, 126, 1, 8>;    // 9 image rows x 384 channels, K = 9 x 384, 8 epilogue warps
+using DalignCfg = GemmCfg<192, 1, 4, 2, 128, 1, 8>;  // g_s tile 128 x 192 (K = 384)
 using ConvWgradCfg = GemmNtCfg<3, false, 192, 0, 3, 112>;  // dW tile 128(co) x 192(ci), 8 image rows per stage
 using AlignWgradCfg = GemmNtCfg<3, false, 192, 0, 4>;      // g_W_align tile 128 x 192
 
