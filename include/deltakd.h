@@ -233,7 +233,7 @@ DKD_API int dkd_saliency_cls_score(const void* xq, int64_t xq_stride, const void
  * positive.  Vk_out[l] (fp32 [rank, Dt]) and S_out[l] (fp32 [rank], singular values) are optional outputs for
  * sign alignment and inspection; sweeps_out (int[n_layers], device) receives the Jacobi sweep counts.
  * s, t, W, bias, g_*, Vk_out, S_out are HOST arrays of n_layers device pointers (n_layers <= 8).
- * Built for Ds = 192, Dt = 384, rank <= 128.  The eigensolver is one cooperative launch (needs 12*n_layers
+ * Built for Ds = 192, Dt = 384, rank <= 128.  The eigensolver is one cooperative launch (24*n_layers co-resident CTAs when that fits 148 SMs, else 12*n_layers
  * co-resident CTAs).
  */
 DKD_API size_t dkd_lrkd_workspace_bytes(int n_layers, int64_t B, int n_tok, int Ds, int Dt, int rank, int dtype,

@@ -115,3 +115,22 @@ def test_lrkd_free_function_and_properties():
         assert abs(l.item() - ref.item()) <= tol_l * abs(ref.item()), (B, dtype, l.item(), ref.item())
         for p, g in zip(proj, refs):
             assert rel_err(p.grad.float(), g) < tol_g
+
+
+def test_lrkd_many_layers_uses_wide_groups():
+    """More than 6 layers would need more than 148 co-resident CTAs with 8-column groups: the eigensolver switches to
+    16-column groups.  Result = sum of the single-layer results (same kernels otherwise), both signs of the basis fixed."""
+    from deltakd_b200 import functional as Fn, synth
+    s_feats, t_feats = synth.make_features(2, 31, layers=range(7))
+    heads = [torch.nn.Linear(192, 16).cuda() for _ in range(7)]
+    s = [s_feats[i].cuda() for i in range(7)]
+    t = [t_feats[i].cuda() for i in range(7)]
+    coef = [0.1 * (i + 1) for i in range(7)]
+    b7 = {}
+    full = Fn.lrkd_layers_loss(s, t, heads, 16, coef, basis_out=b7).item()
+    parts = 0.0
+    for i in range(7):
+        b1 = {}
+        parts += Fn.lrkd_layers_loss([s[i]], [t[i]], [heads[i]], 16, [coef[i]], basis_out=b1).item()
+        assert rel_err(b7["S"][i], b1["S"][0]) < 1e-6
+    assert abs(full - parts) <= 1e-5 * abs(parts), (full, parts)
