@@ -30,7 +30,8 @@ namespace {
 constexpr int kN = 384;              // Dt: order of the Gram matrix
 // Columns per group G: a CTA holds 2G columns and runs one warp per column pair (G warps).  G = 8 (24 CTAs per matrix)
 // is the default — with fewer pairs per SM the fp64 pipe of each SM is less contended and a round is ~20 % shorter
-// than with G = 16; G = 16 (12 CTAs per matrix) is used when 24 * n_layers CTAs would not be co-resident.
+// than with G = 16 (G = 4 measured slower again: 95 grid barriers per sweep); G = 16 (12 CTAs per matrix) is used when
+// 24 * n_layers CTAs would not be co-resident.
 template <int G> struct JacobiCfg {
   static constexpr int CTAS = kN / G / 2;
   static constexpr int THREADS = 32 * G;
