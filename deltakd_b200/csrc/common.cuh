@@ -164,6 +164,40 @@ __device__ __forceinline__ void store_planes32(__nv_bfloat16* hi_ptr, int64_t pl
   }
 }
 
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 — two IEEE fp32 operations per issued instruction) ----------
+// For issue-bound elementwise kernels: the arithmetic is bit-identical to the scalar fmaf / + / *.
+__device__ __forceinline__ unsigned long long f2_pack(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)), "l"(f2_pack(c.x, c.y)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a.x, a.y)), "l"(f2_pack(b.x, b.y)));
+  return f2_unpack(r);
+}
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+
 // ---- reductions ----------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

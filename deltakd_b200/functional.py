@@ -17,12 +17,16 @@ from . import _lib
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+_raw_stream = torch._C._cuda_getCurrentRawStream   # torch.cuda.current_stream() costs ~15 us of Python per call
 
 
-def _ptr(t) -> C.c_void_p:
-    return C.c_void_p(0 if t is None else t.data_ptr())
+def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (plain int: the argtypes convert it)."""
+    return _raw_stream(torch._C._cuda_getDevice())
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
 
 
 def _require_cuda(*tensors) -> None:
@@ -58,16 +62,29 @@ def _rescale_(grad_out: torch.Tensor, *grads):
     if go.dtype != torch.float32 or not go.is_contiguous():
         go = go.to(torch.float32).contiguous()
     live = [g for g in grads if g is not None and g.numel() > 0]
+    fn, go_ptr, st = _lib.lib.dkd_scale_if_not_one, go.data_ptr(), _stream()
     while live:
         a = live.pop(0)
         j = next((k for k, g in enumerate(live) if g.dtype == a.dtype), None)
         b = live.pop(j) if j is not None else None
-        _lib.call("dkd_scale_if_not_one", _ptr(a), a.numel(), _ptr(b), 0 if b is None else b.numel(),
-                  _dtype_code(a), _ptr(go), _stream())
+        rc = fn(a.data_ptr(), a.numel(), None if b is None else b.data_ptr(), 0 if b is None else b.numel(),
+                _DT[a.dtype], go_ptr, st)
+        if rc:
+            _lib.check(rc, "dkd_scale_if_not_one")
     return grads
 
 
 # --------------------------------------------------------------------------- logit losses
+_LOGIT_WS: dict = {}
+
+
+def _logit_ws_bytes(B: int) -> int:
+    n = _LOGIT_WS.get(B)
+    if n is None:
+        n = _LOGIT_WS[B] = int(_lib.lib.dkd_logit_kd_workspace_bytes(B))
+    return n
+
+
 class _LogitKD(torch.autograd.Function):
     @staticmethod
     def forward(ctx, outputs, outputs_kd, teacher_logits, labels, label_kind, kd_kind, smoothing, alpha, tau, parts_out):
@@ -79,8 +96,7 @@ class _LogitKD(torch.autograd.Function):
         g0 = torch.empty_like(outputs) if need_g0 else None
         g1 = torch.empty_like(outputs_kd) if need_g1 else None
         loss3 = torch.empty(3, dtype=torch.float32, device=ref.device)
-        nbytes = _lib.lib.dkd_logit_kd_workspace_bytes(B)
-        ws = _workspace(ref.device, "logit_kd", nbytes)
+        ws = _workspace(ref.device, "logit_kd", _logit_ws_bytes(B))
         _lib.call("dkd_logit_kd_fwdbwd", _ptr(outputs), _ptr(outputs_kd), _ptr(teacher_logits), _ptr(labels),
                   label_kind, kd_kind, B, Cn, dt, float(smoothing), float(alpha), float(tau),
                   _ptr(g0), _ptr(g1), _ptr(loss3), _ptr(ws), ws.numel(), _stream())
