@@ -15,12 +15,35 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict).  On CUDA tensors the two ATen passes are replaced by
+    dkd_layernorm_fwd / _bwd (deltakd_b200/csrc/rowops.cu); under autocast the output is written directly in the
+    autocast dtype.  CPU tensors (the oracle-side harness of bench.py's cpu_baseline and the CPU tests) use ATen."""
+
+    def forward(self, x):
+        if not x.is_cuda:
+            return super().forward(x)
+        from . import functional as Fn
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        return Fn.layer_norm(x, self.weight, self.bias, self.eps, out_dtype)
+
+
+class Linear(nn.Linear):
+    """nn.Linear (same parameters): cuBLAS GEMMs; on CUDA token streams the bias gradient is reduced by dkd_colsum."""
+
+    def forward(self, x):
+        if not x.is_cuda or not torch.is_grad_enabled() or not self.weight.requires_grad:
+            return super().forward(x)
+        from . import functional as Fn
+        return Fn.linear_tokens(x, self.weight, self.bias)
+
+
 class Mlp(nn.Module):
     def __init__(self, dim: int, hidden: int):
         super().__init__()
-        self.fc1 = nn.Linear(dim, hidden)
+        self.fc1 = Linear(dim, hidden)
         self.act = nn.GELU()
-        self.fc2 = nn.Linear(hidden, dim)
+        self.fc2 = Linear(hidden, dim)
 
     def forward(self, x):
         return self.fc2(self.act(self.fc1(x)))
@@ -30,22 +53,23 @@ class Attention(nn.Module):
     def __init__(self, dim: int, num_heads: int):
         super().__init__()
         self.num_heads = num_heads
-        self.qkv = nn.Linear(dim, dim * 3)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv = Linear(dim, dim * 3)
+        self.proj = Linear(dim, dim)
 
     def forward(self, x):
         B, N, C = x.shape
-        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+        # unbind, not qkv[i]: the backward of three selects is three zero-filled qkv-sized tensors and two adds
+        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+        x = F.scaled_dot_product_attention(q, k, v)
         return self.proj(x.transpose(1, 2).reshape(B, N, C))
 
 
 class Block(nn.Module):
     def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0):
         super().__init__()
-        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm1 = LayerNorm(dim, eps=1e-6)
         self.attn = Attention(dim, num_heads)
-        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.norm2 = LayerNorm(dim, eps=1e-6)
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x):
@@ -64,12 +88,12 @@ class DeiT(nn.Module):
         self.patch = patch
         # non-overlapping 16x16 patches: the stride-16 convolution is a GEMM over unfolded patches (same parameters,
         # [D, 3*16*16] weight) — cuDNN's strided-conv kernel is ~5x slower than the GEMM at these shapes
-        self.patch_embed = nn.Linear(3 * patch * patch, embed_dim)
+        self.patch_embed = Linear(3 * patch * patch, embed_dim)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim)) if distilled else None
         self.pos_embed = nn.Parameter(torch.randn(1, n + (2 if distilled else 1), embed_dim) * 0.02)
         self.blocks = nn.ModuleList([Block(embed_dim, num_heads) for _ in range(depth)])
-        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.norm = LayerNorm(embed_dim, eps=1e-6)
         self.head = nn.Linear(embed_dim, num_classes)
         self.head_dist = nn.Linear(embed_dim, num_classes) if distilled else None
 

@@ -244,6 +244,29 @@ DKD_API int dkd_lrkd_fwdbwd(int n_layers, const void* const* s, const void* cons
                             float* const* g_W, float* const* g_b, float* loss, float* const* Vk_out, float* const* S_out,
                             int* sweeps_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row operations of the token streams that feed the loss path (the callers of the path).
+ * The reference builds student and teacher with timm 0.9.12 (model/models.py:59-74): every block is
+ * x + attn(LayerNorm(x)), x + mlp(LayerNorm(x)) with nn.LayerNorm(eps=1e-6); these replace ATen's
+ * native_layer_norm / native_layer_norm_backward and the bias-gradient `sum(0)` of nn.Linear on [B*197, D] streams.
+ *
+ *   dkd_layernorm_fwd : y[m,:] = (x[m,:] - mean_m) * rstd_m * gamma + beta,  rstd = 1/sqrt(var + eps) (biased var);
+ *                       x [M, D] x_dtype, gamma / beta [D] p_dtype (beta may be NULL), y [M, D] y_dtype,
+ *                       mean / rstd fp32 [M] (both NULL for inference).  D % 4 == 0, D <= 1024.
+ *   dkd_layernorm_bwd : dx (x_dtype, may be NULL), dgamma, dbeta (fp32 [D], may be NULL) from dy (dy_dtype), x, gamma,
+ *                       mean, rstd; overwrites.  D % 4 == 0, D <= 512.  Deterministic (fixed-order column folds).
+ *   dkd_colsum        : out[n] = sum_m a[m, n], a [M, N] dtype, out fp32 [N].  N % 8 == 0, N <= 2048.  Deterministic.
+ */
+DKD_API int dkd_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t M, int D, int x_dtype, int p_dtype,
+                              int y_dtype, float eps, void* y, float* mean, float* rstd, dkd_stream_t stream);
+DKD_API size_t dkd_layernorm_bwd_workspace_bytes(int64_t M, int D);
+DKD_API int dkd_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t M,
+                              int D, int dy_dtype, int x_dtype, int p_dtype, void* dx, float* dgamma, float* dbeta,
+                              void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+DKD_API size_t dkd_colsum_workspace_bytes(int64_t M, int N);
+DKD_API int dkd_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* workspace, size_t workspace_bytes,
+                       dkd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
