@@ -433,7 +433,8 @@ class DeiTKDStep(Workload):
     student deit_tiny_distilled fwd (bf16 autocast) -> DistillationLoss (frozen deit_small_distilled teacher forward
     inside, once) -> backward -> fused AdamW, DDP gradient all-reduce over NCCL when world > 1.  The models are the
     plain-PyTorch harness of deltakd_b200/deit.py (timm is absent; model code is outside the hot path), random init,
-    synthetic ImageNet-shaped inputs.  Timed eagerly (no CUDA graph): the step contains the optimizer and DDP."""
+    synthetic ImageNet-shaped inputs.  The whole step is captured once into a CUDA graph (DKD_BENCH_STEP_GRAPH=0: eager)
+    and `step` replays it on the step's inputs."""
     name = "deit_tiny_kd_step_soft_b256_bf16"
     dtype = "bf16"
     B, kind = 256, "soft"
@@ -491,15 +492,41 @@ class DeiTKDStep(Workload):
         xs = torch.randn(2, 3, 224, 224, device=self.device)
         ys = torch.softmax(torch.randn(2, 1000, device=self.device), dim=-1)
         self.opt = None
-        self.step((xs, ys), optimize=False)
-        for p_ in self.student.parameters():
-            if p_.grad is None:
-                p_.requires_grad_(False)
-            p_.grad = None
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.model = torch.nn.parallel.DistributedDataParallel(self.student, device_ids=[self.device.index])
-        self.opt = torch.optim.AdamW([p_ for p_ in self.student.parameters() if p_.requires_grad], lr=5e-4, weight_decay=0.05,
-                                     fused=True)
+        self._graph = None
+        ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        use_graph = os.environ.get("DKD_BENCH_STEP_GRAPH", "1") != "0"
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # DDP under whole-step capture must be built (and warmed up) on a side stream
+            self._eager_step((xs, ys), optimize=False)
+            for p_ in self.student.parameters():
+                if p_.grad is None:
+                    p_.requires_grad_(False)
+                p_.grad = None
+            if ddp:
+                self.model = torch.nn.parallel.DistributedDataParallel(self.student, device_ids=[self.device.index])
+            self.opt = torch.optim.AdamW([p_ for p_ in self.student.parameters() if p_.requires_grad], lr=5e-4, weight_decay=0.05,
+                                         fused=True, capturable=use_graph)
+            if use_graph:
+                # The whole step (student fwd, frozen teacher fwd, fused loss, backward, DDP all-reduce, fused AdamW) is
+                # ONE CUDA graph: the loss path never syncs the host, so nothing in the step needs the CPU — eagerly the
+                # ~970 launches of a step cost 18.4 ms of CPU against 16 ms of GPU work.
+                self._sx = torch.randn(self.B, 3, 224, 224, device=self.device)
+                self._sy = torch.softmax(torch.randn(self.B, 1000, device=self.device), dim=-1)
+                for _ in range(11 if ddp else 3):   # DDP needs 11 eager iterations before capture (torch CUDA-graphs notes)
+                    self._eager_step((self._sx, self._sy))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if use_graph:
+            self.opt.zero_grad(set_to_none=True)
+            from deltakd_b200 import _lib
+            g = torch.cuda.CUDAGraph()
+            c0 = _lib.lib.dkd_launch_count()
+            with torch.cuda.graph(g):
+                self._sloss = self._eager_step((self._sx, self._sy), zero=False)
+            self.launches_per_step = int(_lib.lib.dkd_launch_count() - c0)   # libdeltakd kernels inside one replay
+            self._graph = g
+            torch.cuda.synchronize()
 
     def to_device(self, hs):
         return tuple(t.to(self.device, non_blocking=True) for t in hs)
@@ -507,10 +534,10 @@ class DeiTKDStep(Workload):
     def h2d_bytes(self):
         return self.bytes_per_set()
 
-    def step(self, ds, optimize=True):
+    def _eager_step(self, ds, optimize=True, zero=True):
         from deltakd_b200 import forward_with_features
         x, y = ds
-        if optimize:
+        if optimize and zero:
             self.opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             if self.kind in ("soft", "hard"):
@@ -522,6 +549,14 @@ class DeiTKDStep(Workload):
         if optimize:
             self.opt.step()
         return loss
+
+    def step(self, ds, optimize=True):
+        if self._graph is None:
+            return self._eager_step(ds, optimize)
+        self._sx.copy_(ds[0], non_blocking=True)   # the graph reads its static input buffers
+        self._sy.copy_(ds[1], non_blocking=True)
+        self._graph.replay()
+        return self._sloss
 
     op_only = step
 
@@ -697,6 +732,8 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
         windows.append((t0, time.time()))
         ms = e0.elapsed_time(e1)
         launches = _lib.lib.dkd_launch_count() - c0
+        if getattr(w, "_graph", None) is not None:   # replays do not pass through the library's host-side counter
+            launches = w.launches_per_step * K
         loss_val = float(last.item())
         k_ms = ms / K
 
@@ -735,7 +772,8 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
                      ("algorithmic_bytes" if w.bound == "hbm" else "algorithmic_flops"): alg},
     }
     if not getattr(w, "graphable", True):
-        res["timing"] = "eager steps (optimizer + DDP inside), CUDA events, max over ranks"
+        res["timing"] = ("K replays of the whole-step CUDA graph (fwd + loss + bwd + DDP all-reduce + AdamW), CUDA events, max over ranks"
+                         if getattr(w, "_graph", None) is not None else "eager steps (optimizer + DDP inside), CUDA events, max over ranks")
     if w.bound == "hbm" and w.algorithmic_flops():
         res["roofline"]["algorithmic_flops"] = w.algorithmic_flops()
     if hasattr(w, "extra_roofline"):
@@ -771,6 +809,7 @@ def main():
     dev = torch.device("cuda", local)
     if dist_on:
         import torch.distributed as dist
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # required for NCCL collectives inside a captured step
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

@@ -53,6 +53,7 @@ SIGNATURES = {
     "dkd_layernorm_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "dkd_layernorm_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "dkd_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "dkd_head_copy": (_i, [_p, _p, _i64, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p]),
     "dkd_colsum_workspace_bytes": (_sz, [_i64, _i]),
     "dkd_colsum": (_i, [_p, _i64, _i, _i, _p, _p, _sz, _p]),
     "dkd_align_mse_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),

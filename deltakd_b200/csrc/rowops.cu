@@ -245,6 +245,30 @@ __global__ void __launch_bounds__(kRowThreads) colsum_kernel(const T* a, int64_t
   }
 }
 
+// Head-layout copy of attention tensors: dst[b, h, n, 0:hd] = src[b, h, n, 0:hd], each side with its own (b, h, n) element
+// strides, hd contiguous.  Runs are walked in (b, n, h) order, 16 bytes per thread: with a token-major side ([B, N, H, hd])
+// that side is fully coalesced and the other moves whole 128-byte head rows.
+struct HeadCopyParams {
+  const char* src;
+  char* dst;
+  int64_t sb, sh, sn, db, dh, dn;   // BYTE strides
+  int64_t runs;                     // B * N * H
+  int H, N, vec_per_run;            // 16-byte vectors per run (hd * elt / 16)
+};
+__global__ void __launch_bounds__(256) head_copy_kernel(HeadCopyParams p) {
+  const int64_t total = p.runs * p.vec_per_run;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t run = i / p.vec_per_run;
+    const int v = (int)(i - run * p.vec_per_run);
+    const int h = (int)(run % p.H);
+    const int64_t bn = run / p.H;
+    const int n = (int)(bn % p.N);
+    const int64_t b = bn / p.N;
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.src + b * p.sb + h * p.sh + n * p.sn) + v);
+    *(reinterpret_cast<uint4*>(p.dst + b * p.db + h * p.dh + n * p.dn) + v) = w;
+  }
+}
+
 int row_grid(int64_t M) {
   const int64_t ctas = (M + kRowWarps - 1) / kRowWarps;
   return (int)(ctas < kMaxRowCtas ? ctas : kMaxRowCtas);
@@ -348,6 +372,31 @@ static int colsum_grid(int64_t M, int N, int64_t* rows_per_cta) {
   if (rows < min_rows) rows = min_rows;
   *rows_per_cta = rows;
   return (int)((M + rows - 1) / rows);
+}
+
+int dkd_head_copy(const void* src, void* dst, int64_t B, int H, int N, int hd, int elt_bytes, int64_t src_b, int64_t src_h,
+                  int64_t src_n, int64_t dst_b, int64_t dst_h, int64_t dst_n, dkd_stream_t stream) {
+  using namespace dkd;
+  int rc = dkd_check_device();
+  if (rc != DKD_OK) return rc;
+  DKD_REQUIRE(B >= 0 && H > 0 && N > 0 && hd > 0 && (elt_bytes == 2 || elt_bytes == 4), DKD_E_SHAPE, "dkd_head_copy: bad shape");
+  DKD_REQUIRE(((int64_t)hd * elt_bytes) % 16 == 0, DKD_E_SHAPE, "dkd_head_copy: head rows must be multiples of 16 bytes");
+  DKD_REQUIRE(src && dst, DKD_E_SHAPE, "dkd_head_copy: null pointer");
+  const int64_t strides[6] = {src_b, src_h, src_n, dst_b, dst_h, dst_n};
+  for (int i = 0; i < 6; ++i)
+    DKD_REQUIRE(strides[i] >= 0 && (strides[i] * elt_bytes) % 16 == 0, DKD_E_ALIGN, "dkd_head_copy: strides must be multiples of 16 bytes");
+  DKD_REQUIRE(aligned16(src) && aligned16(dst), DKD_E_ALIGN, "dkd_head_copy: 16-byte alignment");
+  if (B == 0) return DKD_OK;
+  HeadCopyParams p;
+  p.src = reinterpret_cast<const char*>(src); p.dst = reinterpret_cast<char*>(dst);
+  p.sb = src_b * elt_bytes; p.sh = src_h * elt_bytes; p.sn = src_n * elt_bytes;
+  p.db = dst_b * elt_bytes; p.dh = dst_h * elt_bytes; p.dn = dst_n * elt_bytes;
+  p.runs = B * N * H; p.H = H; p.N = N; p.vec_per_run = hd * elt_bytes / 16;
+  const int64_t total = p.runs * p.vec_per_run;
+  const int64_t want = (total + 256 * 4 - 1) / (256 * 4);          // ~4 vectors per thread
+  const int grid = (int)(want < 1 ? 1 : want > kNumSMs * 16 ? kNumSMs * 16 : want);
+  head_copy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("dkd_head_copy");
 }
 
 size_t dkd_colsum_workspace_bytes(int64_t M, int N) {

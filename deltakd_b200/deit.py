@@ -58,8 +58,12 @@ class Attention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        # unbind, not qkv[i]: the backward of three selects is three zero-filled qkv-sized tensors and two adds
-        q, k, v = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4).unbind(0)
+        qkv = self.qkv(x)
+        if x.is_cuda:   # head relayouts by dkd_head_copy (ATen: strided copies, and select-backward fills / cat in backward)
+            from . import functional as Fn
+            q, k, v = Fn.split_qkv(qkv, self.num_heads)
+            return self.proj(Fn.merge_heads(F.scaled_dot_product_attention(q, k, v)))
+        q, k, v = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4).unbind(0)
         x = F.scaled_dot_product_attention(q, k, v)
         return self.proj(x.transpose(1, 2).reshape(B, N, C))
 

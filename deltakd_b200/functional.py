@@ -613,3 +613,87 @@ def linear_tokens(x, weight, bias):
     if N % 8 != 0 or N > 2048 or x.numel() // x.shape[-1] < 1024:
         return torch.nn.functional.linear(x, weight, bias)   # small / odd shapes (classifier heads): library path
     return _LinearTokens.apply(x, weight, bias)
+
+
+def _head_copy(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[b,h,n,:] = src[b,h,n,:] for two [B,H,N,hd] views with arbitrary (b,h,n) strides and contiguous head rows."""
+    B, H, N, hd = src.shape
+    sb, sh, sn, s1 = src.stride()
+    db, dh, dn, d1 = dst.stride()
+    if (s1 != 1 and hd > 1) or (d1 != 1 and hd > 1) or src.dtype != dst.dtype or dst.shape != src.shape:
+        raise ValueError("head copy needs same-shaped views with contiguous head rows")
+    _lib.call("dkd_head_copy", src.data_ptr(), dst.data_ptr(), B, H, N, hd, src.element_size(), sb, sh, sn, db, dh, dn, _stream())
+
+
+def _head_copy_ok(t: torch.Tensor) -> bool:
+    e = t.element_size()
+    return (t.is_cuda and t.dim() == 4 and t.stride(3) == 1 and (t.shape[3] * e) % 16 == 0 and t.data_ptr() % 16 == 0
+            and all((s * e) % 16 == 0 for s in t.stride()[:3]))
+
+
+class _MergeHeads(torch.autograd.Function):
+    """[B,H,N,hd] attention output (any head-row strides) -> [B,N,H*hd] contiguous, one dkd_head_copy each way."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, H, N, hd = x.shape
+        y = torch.empty(B, N, H * hd, dtype=x.dtype, device=x.device)
+        _head_copy(x, y.view(B, N, H, hd).transpose(1, 2))
+        ctx.shape = (B, H, N, hd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, N, hd = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty(B, H, N, hd, dtype=dy.dtype, device=dy.device)
+        _head_copy(dy.view(B, N, H, hd).transpose(1, 2), dx)
+        return dx
+
+
+class _SplitQKV(torch.autograd.Function):
+    """Packed projections [B,N,3*H*hd] -> q, k, v as [B,H,N,hd] views; the backward writes dq, dk, dv straight into one
+    packed gradient (three dkd_head_copy launches) instead of ATen's select-backward zero fills / cat."""
+
+    @staticmethod
+    def forward(ctx, qkv, H):
+        B, N, C3 = qkv.shape
+        hd = C3 // (3 * H)
+        ctx.dims = (B, N, H, hd)
+        v5 = qkv.view(B, N, 3, H, hd)
+        return tuple(v5[:, :, i].transpose(1, 2) for i in range(3))
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        B, N, H, hd = ctx.dims
+        ref = next(g for g in (dq, dk, dv) if g is not None)
+        out = torch.empty(B, N, 3, H, hd, dtype=ref.dtype, device=ref.device)
+        for i, g in enumerate((dq, dk, dv)):
+            dst = out[:, :, i].transpose(1, 2)
+            if g is None:
+                dst.zero_()
+            else:
+                _head_copy(g if _head_copy_ok(g) else g.contiguous(), dst)
+        return out.view(B, N, 3 * H * hd), None
+
+
+def split_qkv(qkv: torch.Tensor, num_heads: int):
+    """q, k, v [B,H,N,hd] views of a packed [B,N,3*C] projection (see _SplitQKV)."""
+    _require_cuda(qkv)
+    hd = qkv.shape[-1] // (3 * num_heads)
+    if not qkv.is_contiguous() or (hd * qkv.element_size()) % 16 != 0:
+        B, N, _ = qkv.shape
+        return qkv.reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    return _SplitQKV.apply(qkv, num_heads)
+
+
+def merge_heads(x: torch.Tensor) -> torch.Tensor:
+    """[B,H,N,hd] -> [B,N,H*hd] (a view when the strides already allow it)."""
+    _require_cuda(x)
+    B, H, N, hd = x.shape
+    t = x.transpose(1, 2)
+    if t.is_contiguous():
+        return t.reshape(B, N, H * hd)
+    if not _head_copy_ok(x):
+        return t.reshape(B, N, H * hd)
+    return _MergeHeads.apply(x)

@@ -263,6 +263,12 @@ DKD_API size_t dkd_layernorm_bwd_workspace_bytes(int64_t M, int D);
 DKD_API int dkd_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd, int64_t M,
                               int D, int dy_dtype, int x_dtype, int p_dtype, void* dx, float* dgamma, float* dbeta,
                               void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+/*   dkd_head_copy     : dst[b,h,n,0:hd] = src[b,h,n,0:hd] with independent (b,h,n) ELEMENT strides per side, hd contiguous
+ *                       (hd * elt_bytes and all strides multiples of 16 bytes): the [B,H,N,hd] <-> [B,N,H,hd] relayouts
+ *                       around scaled-dot-product attention (head merge, packed-qkv gradient assembly).
+ */
+DKD_API int dkd_head_copy(const void* src, void* dst, int64_t B, int H, int N, int hd, int elt_bytes, int64_t src_b, int64_t src_h,
+                          int64_t src_n, int64_t dst_b, int64_t dst_h, int64_t dst_n, dkd_stream_t stream);
 DKD_API size_t dkd_colsum_workspace_bytes(int64_t M, int N);
 DKD_API int dkd_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* workspace, size_t workspace_bytes,
                        dkd_stream_t stream);

@@ -113,3 +113,31 @@ def test_deit_harness_fused_row_ops_match_aten():
                  "blocks.3.mlp.fc2.weight", "pos_embed"):
         g1, g2 = dict(m.named_parameters())[name].grad, dict(ref.named_parameters())[name].grad
         assert rel_err(g1, g2) < 8e-2, (name, rel_err(g1, g2))
+
+
+@pytest.mark.parametrize("B,H,N,hd,dt", [(2, 3, 197, 64, torch.bfloat16), (3, 6, 198, 64, torch.bfloat16), (1, 1, 5, 8, torch.float32),
+                                         (4, 3, 197, 64, torch.float32)])
+def test_attention_head_relayouts_are_exact(B, H, N, hd, dt):
+    """split_qkv / merge_heads (dkd_head_copy) are pure relayouts: forward and backward bit-identical to ATen's."""
+    from deltakd_b200 import functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + N)
+    qkv = torch.randn(B, N, 3 * H * hd, device="cuda", generator=g).to(dt)
+    a = qkv.clone().requires_grad_(True)
+    b = qkv.clone().requires_grad_(True)
+    q1, k1, v1 = Fn.split_qkv(a, H)
+    q2, k2, v2 = b.reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    for u, w in ((q1, q2), (k1, k2), (v1, v2)):
+        assert u.shape == (B, H, N, hd) and torch.equal(u, w)
+    # a [B,H,N,hd]-contiguous "attention output" built from the three parts, merged back to token-major
+    o1 = (q1 * 2 + k1).contiguous() + v1
+    o2 = (q2 * 2 + k2).contiguous() + v2
+    y1 = Fn.merge_heads(o1)
+    y2 = o2.transpose(1, 2).reshape(B, N, H * hd)
+    assert y1.shape == (B, N, H * hd) and y1.is_contiguous() and torch.equal(y1, y2)
+    dy = torch.randn(B, N, H * hd, device="cuda", generator=g).to(dt)
+    y1.backward(dy)
+    y2.backward(dy)
+    assert torch.equal(a.grad, b.grad)
+    # merge of an already token-major tensor is a view
+    z = torch.randn(B, N, H, hd, device="cuda").to(dt).transpose(1, 2)
+    assert Fn.merge_heads(z).data_ptr() == z.data_ptr()
