@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(kRowThreads, NCH <= 2 ? 3 : 2) layernorm_bwd_k
   }
 }
 
-// out[k] = sum_{c < n} partial[c][k], k < width.  32 columns x 8 row lanes per CTA: lane q sums partials q, q+8, ...
-// in 4 independent chains, the 8 lanes are combined through shared memory — all in a fixed order (deterministic).
+// out[k] = sum_{c < n} partial[c][k], k < width.  32 columns x 32 row lanes per CTA: lane q sums partials q, q+32, ...
+// in 4 independent chains, the 32 lanes are combined through shared memory — all in a fixed order (deterministic).
 // (One thread per column walking all n partials is a chain of n/4 dependent L2 round trips: 23 us for n = 592.)
 // out_a gets columns [0, split), out_b columns [split, width) (dgamma | dbeta); either may be null.
-constexpr int kFoldCols = 32, kFoldLanes = 8;
+constexpr int kFoldCols = 32, kFoldLanes = 32;
 __global__ void __launch_bounds__(kFoldCols * kFoldLanes) fold_columns_kernel(const float* partial, int n, int width, int split,
                                                                               float* out_a, float* out_b) {
   __shared__ float s_f[kFoldLanes][kFoldCols];
