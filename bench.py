@@ -41,12 +41,14 @@ METRIC = "distill-loss fwd+bwd samples/s"
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of each workload's dominant kernel(s), per launch of the fused op, from
-# the `ncu --set full` captures summarised in profiles/r1m_ncu_summary.txt (same command line, B200).  Gradient /
-# plane WRITES of the small workloads stay in the 126 MB L2 until evicted, so traffic can be below the algorithmic bytes.
-NCU_TRAFFIC = {
-    "soft_kd_logits_b256_c1000_bf16": (2.085e6 + 0.0, "logit_kd_kernel"),
-    "curkd_early_3layers_b512_f32": (3 * ((231.6 + 119.2) + (154.5 + 44.3) + (231.5 + 3.7)) * 1e6, "3 layers x (fwd + dgrad + wgrad GEMM)"),
-    "wasskd_l1_b512_f32": (3 * (308.4 + 127.5) * 1e6, "3 x wass_sort_kernel (GEMMs as CurKD)"),
+# the `ncu --set full` captures summarised under profiles/ (same command line, B200).  Gradient / plane WRITES of the
+# small workloads stay in the 126 MB L2 until evicted, so traffic can be below the algorithmic bytes.
+NCU_TRAFFIC = {   # workload -> (bytes, kernels, summary file)
+    "soft_kd_logits_b256_c1000_bf16": (2.068e6 + 0.0, "logit_kd_kernel", "profiles/r2p_ncu_summary.txt"),
+    "soft_kd_logits_b16384_c1000_bf16": ((131.1 + 38.48) * 1e6, "logit_kd_kernel", "profiles/r2p_ncu_summary.txt"),
+    "curkd_early_3layers_b512_f32": (3 * ((231.6 + 119.2) + (154.5 + 44.3) + (231.5 + 3.7)) * 1e6, "3 layers x (fwd + dgrad + wgrad GEMM)",
+                                     "profiles/r1m_ncu_summary.txt"),
+    "wasskd_l1_b512_f32": (3 * (308.4 + 127.5) * 1e6, "3 x wass_sort_kernel (GEMMs as CurKD)", "profiles/r1m_ncu_summary.txt"),
 }
 
 
@@ -766,8 +768,8 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
         "roofline": {"bound": w.bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                     "traffic": NCU_TRAFFIC.get(w.name, (None, None))[0], "traffic_source": (
-                         f"ncu dram bytes, {NCU_TRAFFIC[w.name][1]} (profiles/r1m_ncu_summary.txt)" if w.name in NCU_TRAFFIC else None),
+                     "traffic": NCU_TRAFFIC.get(w.name, (None, None, None))[0], "traffic_source": (
+                         f"ncu dram bytes, {NCU_TRAFFIC[w.name][1]} ({NCU_TRAFFIC[w.name][2]})" if w.name in NCU_TRAFFIC else None),
                      "kernel": w.dominant, "kernel_us": k_ms * 1e3, "peak_source": pk["src"],
                      ("algorithmic_bytes" if w.bound == "hbm" else "algorithmic_flops"): alg},
     }
