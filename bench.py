@@ -474,12 +474,13 @@ class DeiTKDStep(Workload):
         from deltakd_b200 import DistillationLoss, call_base_loss, deit, heads as H
         args = self.make_args()
         torch.manual_seed(0)
-        teacher = deit.create_model("deit_small_distilled_patch16_224").to(device).eval()
+        row_ops = "dkd" if device.type == "cuda" else "aten"   # the CPU model is the reference-style harness of cpu_baseline
+        teacher = deit.create_model("deit_small_distilled_patch16_224", row_ops=row_ops).to(device).eval()
         for p_ in teacher.parameters():
             p_.requires_grad_(False)
         if device.type == "cuda":
             teacher = teacher.to(torch.bfloat16)   # frozen: keep bf16 weights instead of autocast-casting them every step
-        student = deit.create_model(self.student_name).to(device)
+        student = deit.create_model(self.student_name, row_ops=row_ops).to(device)
         H.attach_distillation_heads(student, teacher, args, self.student_name)
         student = student.to(device).train()
         return args, teacher, student, DistillationLoss, call_base_loss

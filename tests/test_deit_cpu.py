@@ -26,3 +26,15 @@ def test_hooks_capture_pre_residual_mlp_outputs():
     assert feats[11].shape == (1, 197, 192) and feats[11].requires_grad
     assert t.embed_dim == 384 and s.embed_dim == 192
     assert forward_with_features(torch.nn.Linear(3, 3), x) == (None, None)   # models.py:182-183
+
+
+def test_dkd_row_ops_model_has_same_parameters_and_no_cpu_path():
+    import pytest
+    a = deit.create_model("deit_tiny_distilled_patch16_224", num_classes=10, row_ops="aten")
+    d = deit.create_model("deit_tiny_distilled_patch16_224", num_classes=10, row_ops="dkd")
+    assert [(k, tuple(v.shape)) for k, v in a.state_dict().items()] == [(k, tuple(v.shape)) for k, v in d.state_dict().items()]
+    d.load_state_dict(a.state_dict())
+    with pytest.raises(RuntimeError):          # libdeltakd_sm100's row ops take CUDA tensors only: loud failure, no fallback
+        d(torch.randn(1, 3, 224, 224))
+    with pytest.raises(ValueError):
+        deit.create_model("deit_tiny_patch16_224", row_ops="triton")

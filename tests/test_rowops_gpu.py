@@ -79,25 +79,15 @@ def test_deit_harness_fused_row_ops_match_aten():
     import torch.nn as nn
     from deltakd_b200 import deit
     torch.manual_seed(0)
-    m = deit.create_model("deit_tiny_distilled_patch16_224", num_classes=100).cuda().train()
+    m = deit.create_model("deit_tiny_distilled_patch16_224", num_classes=100, row_ops="dkd").cuda().train()
     m.set_distilled_training(True)
-    ref = deit.create_model("deit_tiny_distilled_patch16_224", num_classes=100).cuda().train()
+    ref = deit.create_model("deit_tiny_distilled_patch16_224", num_classes=100, row_ops="aten").cuda().train()
     ref.set_distilled_training(True)
-    ref.load_state_dict(m.state_dict())
-
-    def to_aten(mod):
-        for name, child in mod.named_children():
-            if isinstance(child, deit.LayerNorm):
-                new = nn.LayerNorm(child.normalized_shape, eps=child.eps).cuda()
-                new.load_state_dict(child.state_dict())
-                setattr(mod, name, new)
-            elif isinstance(child, deit.Linear):
-                new = nn.Linear(child.in_features, child.out_features).cuda()
-                new.load_state_dict(child.state_dict())
-                setattr(mod, name, new)
-            else:
-                to_aten(child)
-    to_aten(ref)
+    ref.load_state_dict(m.state_dict())            # same parameter names and shapes
+    assert isinstance(m.blocks[0].norm1, deit.LayerNorm) and type(ref.blocks[0].norm1) is nn.LayerNorm
+    with pytest.raises(RuntimeError):
+        m.blocks[0].norm1.cpu()(torch.randn(2, 197, 192))   # dkd modules have no CPU path
+    m.cuda()
     x = torch.randn(8, 3, 224, 224, device="cuda")
     outs = []
     for model in (m, ref):
