@@ -501,9 +501,12 @@ class DeiTKDStep(Workload):
         # --workload (verified at 2 and 8 GPUs); as one of several "extras" in a multi-rank process it runs eagerly —
         # capturing a second DDP graph on the same process group after the first was destroyed is not a tested sequence.
         use_graph = os.environ.get("DKD_BENCH_STEP_GRAPH", "1") != "0" and (not ddp or getattr(self, "allow_ddp_graph", True))
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):   # DDP under whole-step capture must be built (and warmed up) on a side stream
+        import contextlib
+        side = torch.cuda.Stream() if use_graph else None
+        if use_graph:
+            side.wait_stream(torch.cuda.current_stream())
+        # DDP under whole-step capture must be built (and warmed up) on a side stream; the eager path stays on the current one
+        with (torch.cuda.stream(side) if use_graph else contextlib.nullcontext()):
             self._eager_step((xs, ys), optimize=False)
             for p_ in self.student.parameters():
                 if p_.grad is None:
@@ -521,7 +524,8 @@ class DeiTKDStep(Workload):
                 self._sy = torch.softmax(torch.randn(self.B, 1000, device=self.device), dim=-1)
                 for _ in range(11 if ddp else 3):   # DDP needs 11 eager iterations before capture (torch CUDA-graphs notes)
                     self._eager_step((self._sx, self._sy))
-        torch.cuda.current_stream().wait_stream(side)
+        if use_graph:
+            torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         if use_graph:
             self.opt.zero_grad(set_to_none=True)
