@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py â€” DeltaKD distillation-loss hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference] [--no-extras]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference] [--no-extras | --extras]
 
 A "step" is one pass of the hot path (loss forward + backward through
 `deltakd_b200.DistillationLoss`) over one batch of synthetic teacher/student outputs.
@@ -16,7 +16,8 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md Â
   cpu_baseline the CPU oracle (restatement of the reference's PyTorch loss, `kind: "port"`) timed on
                this box's host cores on a bounded sample of the same workload
   workloads    the other BASELINE.json configs (feature losses at their full batch sizes), each with
-               value / e2e / roofline / cpu_baseline, measured the same way (skipped by --no-extras)
+               value / e2e / roofline / cpu_baseline, measured the same way (single-GPU runs; skipped by --no-extras,
+               forced under torchrun by --extras)
   --impl reference : the reference arm = the same CPU oracle with all host threads (the reference is
                pure PyTorch; /root/reference does not exist on the GPU box)
 """
@@ -804,6 +805,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only")
+    ap.add_argument("--extras", action="store_true", help="also run the other workloads under torchrun (default: single-GPU runs only)")
     args = ap.parse_args()
     w_cls = WORKLOADS[args.workload]
     if args.steps is None:
@@ -840,7 +842,10 @@ def main():
 
     head, windows = measure(w_cls(dev, rank), args.steps, W, world, barrier, allmax, pk, with_cpu)
     extras = []
-    if not args.no_extras and w_cls is HEADLINE:
+    # The other configs are reported beside the headline on single-GPU runs; a multi-rank run measures the selected
+    # workload only unless --extras is given (keeps the 1 -> 8 scaling runs short; per-workload multi-GPU lines are
+    # taken with --workload, see profiles/).
+    if not args.no_extras and w_cls is HEADLINE and (world == 1 or args.extras):
         for cls in EXTRAS:
             try:
                 wl = cls(dev, rank)
