@@ -63,6 +63,12 @@ def _rescale_(grad_out: torch.Tensor, *grads):
         go = go.to(torch.float32).contiguous()
     live = [g for g in grads if g is not None and g.numel() > 0]
     fn, go_ptr, st = _lib.lib.dkd_scale_if_not_one, go.data_ptr(), _stream()
+    if len(live) == 2 and live[0].dtype == live[1].dtype:     # the logit losses: both gradients in one launch
+        a, b = live
+        rc = fn(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), _DT[a.dtype], go_ptr, st)
+        if rc:
+            _lib.check(rc, "dkd_scale_if_not_one")
+        return grads
     while live:
         a = live.pop(0)
         j = next((k for k, g in enumerate(live) if g.dtype == a.dtype), None)
@@ -76,6 +82,16 @@ def _rescale_(grad_out: torch.Tensor, *grads):
 
 # --------------------------------------------------------------------------- logit losses
 _LOGIT_WS: dict = {}
+_LOGIT_FN = _lib.lib.dkd_logit_kd_fwdbwd   # bound once: this call is on the per-step latency path of configs[1]
+
+
+def _plain(t: torch.Tensor) -> torch.Tensor:
+    """`t` without autograd history (detach() only when there is one: it costs ~4 us of host time)."""
+    return t.detach() if t.requires_grad else t
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
 
 
 def _logit_ws_bytes(B: int) -> int:
@@ -97,9 +113,11 @@ class _LogitKD(torch.autograd.Function):
         g1 = torch.empty_like(outputs_kd) if need_g1 else None
         loss3 = torch.empty(3, dtype=torch.float32, device=ref.device)
         ws = _workspace(ref.device, "logit_kd", _logit_ws_bytes(B))
-        _lib.call("dkd_logit_kd_fwdbwd", _ptr(outputs), _ptr(outputs_kd), _ptr(teacher_logits), _ptr(labels),
-                  label_kind, kd_kind, B, Cn, dt, float(smoothing), float(alpha), float(tau),
-                  _ptr(g0), _ptr(g1), _ptr(loss3), _ptr(ws), ws.numel(), _stream())
+        rc = _LOGIT_FN(_ptr(outputs), _ptr(outputs_kd), _ptr(teacher_logits), _ptr(labels),
+                       label_kind, kd_kind, B, Cn, dt, float(smoothing), float(alpha), float(tau),
+                       _ptr(g0), _ptr(g1), loss3.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        if rc:
+            _lib.check(rc, "dkd_logit_kd_fwdbwd")
         ctx.grads = (g0, g1)
         parts_out.append(loss3)  # {total, base, kd}, detached side channel for logging
         return loss3[0]
@@ -146,14 +164,14 @@ def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, 
             teacher_logits = teacher_logits.to(ref.dtype)
         if outputs_kd.dtype != ref.dtype:
             raise TypeError("outputs and outputs_kd must share a dtype")
-        teacher_logits = teacher_logits.detach().contiguous()
-        outputs_kd = outputs_kd.contiguous()
+        teacher_logits = _contig(_plain(teacher_logits))
+        outputs_kd = _contig(outputs_kd)
     else:
         outputs_kd = teacher_logits = None
     if outputs is not None:
-        outputs = outputs.contiguous()
+        outputs = _contig(outputs)
     if labels is not None:
-        labels = labels.detach().contiguous()
+        labels = _contig(_plain(labels))
     parts = []
     total = _LogitKD.apply(outputs, outputs_kd, teacher_logits, labels, lk, kk, smoothing, alpha, tau, parts)
     return (total, parts[0]) if return_parts else total

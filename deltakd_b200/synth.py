@@ -95,8 +95,10 @@ class FeatureReplayModel(nn.Module):
         self.logits = None
 
     def set_outputs(self, logits, feats):
-        self.logits = logits
-        self._has_feats = feats is not None
+        # plain attributes, set past nn.Module.__setattr__ (its parameter / buffer / module checks cost ~4 us per
+        # assignment — this runs once per step inside the end-to-end timed region of bench.py)
+        object.__setattr__(self, "logits", logits)
+        object.__setattr__(self, "_has_feats", feats is not None)
         if feats is None and not getattr(self, "_feats_set", False):
             return                                  # logits-only replay: nothing to reset
         self._feats_set = feats is not None
