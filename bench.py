@@ -41,16 +41,21 @@ L2_BYTES = 126 * 1024 * 1024
 METRIC = "distill-loss fwd+bwd samples/s"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of each workload's dominant kernel(s), per launch of the fused op, from
-# the `ncu --set full` captures summarised under profiles/ (same command line, B200).  Gradient / plane WRITES of the
-# small workloads stay in the 126 MB L2 until evicted, so traffic can be below the algorithmic bytes.
-NCU_TRAFFIC = {   # workload -> (bytes, kernels, summary file)
-    "soft_kd_logits_b256_c1000_bf16": (2.068e6 + 0.0, "logit_kd_kernel", "profiles/r2p_ncu_summary.txt"),
-    "soft_kd_logits_b16384_c1000_bf16": ((131.1 + 38.48) * 1e6, "logit_kd_kernel", "profiles/r2p_ncu_summary.txt"),
-    "curkd_early_3layers_b512_f32": (3 * ((231.6 + 119.2) + (154.5 + 44.3) + (231.5 + 3.7)) * 1e6, "3 layers x (fwd + dgrad + wgrad GEMM)",
-                                     "profiles/r1m_ncu_summary.txt"),
-    "wasskd_l1_b512_f32": (3 * (308.4 + 127.5) * 1e6, "3 x wass_sort_kernel (GEMMs as CurKD)", "profiles/r1m_ncu_summary.txt"),
-}
+def ncu_traffic():
+    """workload -> {"bytes": dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel one call of the fused op
+    launches, "kernels": [...], "source": file}: written by tools/ncu_traffic.py from an `ncu` pass of
+    `bench.py --ncu-op <workload>` on the final build (profiles/ncu_traffic.json).  Gradient / plane WRITES of the small
+    workloads stay in the 126 MB L2 until evicted, so traffic can be below the algorithmic bytes."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except ValueError:
+            return {}
+    return {}
+
+
+NCU_TRAFFIC = ncu_traffic()
 
 
 def peaks():
@@ -131,6 +136,26 @@ class Workload:
     def algorithmic_flops(self):
         return 0.0
 
+    # ---- parity gate: before anything is timed, the step's loss on a sub-batch is checked against the CPU oracle
+    parity_rtol = 1e-5      # the north-star loss gate in fp32; bf16 workloads state 2e-2
+
+    def slice_host(self, hs, n):
+        raise NotImplementedError
+
+    def parity(self):
+        """{"batch", "loss", "oracle", "rel_err", "rtol", "ok"}: loss of one step through the public API on the first
+        `cpu_B` samples of input set 0 against the fp32 oracle on the same samples (rank 0 only)."""
+        Bc = min(self.cpu_B or self.B, self.B)
+        hs = self.slice_host(self.host_sets(1, B=self.B)[0], Bc)
+        full_B, self.B = self.B, Bc
+        try:
+            got = float(self.step(self.to_device(hs)).item())
+        finally:
+            self.B = full_B
+        want = float(self.cpu_step(self.cpu_prepare(hs)).item())
+        rel = abs(got - want) / max(abs(want), 1e-30)
+        return {"batch": Bc, "loss": got, "oracle": want, "rel_err": rel, "rtol": self.parity_rtol, "ok": rel <= self.parity_rtol}
+
 
 class LogitKD(Workload):
     """configs[1]: base SoftTargetCE + soft-KD (tau 3, alpha 0.1) on DeiT-Tiny logits, B=256, C=1000, bf16."""
@@ -157,6 +182,9 @@ class LogitKD(Workload):
             sets.append(_pin(torch.stack([z, zk, zt, y]).to(self.tdtype)))
         return sets
 
+    def slice_host(self, hs, n):
+        return hs[:, :n].contiguous()
+
     def setup(self):
         from deltakd_b200 import DistillationLoss, call_base_loss, synth
         self.args = synth.default_args()
@@ -175,7 +203,7 @@ class LogitKD(Workload):
         z, zk, zt, y = ds
         self.teacher.set_outputs(zt, None)
         z.grad = zk.grad = None
-        loss = self.crit(self.inputs, (z, zk), None, None, y, self.args)
+        loss = self.crit(self.inputs if z.shape[0] == self.inputs.shape[0] else self.inputs[:z.shape[0]], (z, zk), None, None, y, self.args)
         loss.backward()
         return loss
 
@@ -207,6 +235,19 @@ class LogitKDLargeBatch(LogitKD):
     default_steps = 20
 
 
+class LogitKDf32(LogitKD):
+    """configs[1]'s op in the reference's own dtype (fp32 end to end): the same-dtype comparison with the CPU arm."""
+    name = "soft_kd_logits_b256_c1000_f32"
+    dtype = "f32"
+    tdtype = torch.float32
+
+
+class LogitKDf32B8(LogitKDf32):
+    """configs[0]: B = 8 x 1000 classes, fp32 (the reference's CPU-runnable case)."""
+    name = "soft_kd_logits_b8_c1000_f32"
+    B = 8
+
+
 class FeatureKD(Workload):
     """Feature-level losses: student block outputs [B,197,192], teacher [B,198,384], heads on the student."""
     kind = ""
@@ -215,9 +256,24 @@ class FeatureKD(Workload):
     args_kw = {}
     M_TOK = 196
 
+    def __init__(self, device, rank, B=None):
+        super().__init__(device, rank)
+        if B is not None and B != self.B:   # cfg5: the global batch of 1024 split over the ranks (B_loc = 1024 / N)
+            self.name = self.name.replace(f"_b{self.B}_", f"_b{B}_")
+            self.cpu_B = min(self.cpu_B or B, B)
+            self.B = B
+
     def make_args(self):
         from deltakd_b200 import synth
         return synth.default_args(distillation_type=self.kind, **self.args_kw)
+
+    @property
+    def parity_rtol(self):
+        return 1e-5 if self.tdtype == torch.float32 else 2e-2
+
+    def slice_host(self, hs, n):
+        cut = lambda x: None if x is None else x[:n].contiguous()
+        return dict(s=[cut(x) for x in hs["s"]], t=[cut(x) for x in hs["t"]], z=cut(hs["z"]), y=cut(hs["y"]), noise=cut(hs["noise"]))
 
     def bytes_per_set(self):
         return len(self.layers) * self.B * (197 * 192 + 198 * 384) * self.tdtype.itemsize
@@ -271,7 +327,7 @@ class FeatureKD(Workload):
             p.grad = None
         noise = ds["noise"]
         with mock.patch("torch.rand", side_effect=lambda *a, **k: noise):  # fixed mask noise (graph-capturable)
-            loss = self.crit(self.inputs, ds["z"], self.student, ds["s"], ds["y"], self.args)
+            loss = self.crit(self.inputs[:ds["z"].shape[0]], ds["z"], self.student, ds["s"], ds["y"], self.args)
         loss.backward()
         return loss
 
@@ -402,6 +458,32 @@ class LRKD(FeatureKD):
         return Fn.lrkd_layers_loss([ds["s"][0], ds["s"][1], ds["s"][11]], [ds["t"][0], ds["t"][1], ds["t"][11]],
                                    list(self.student.align), a.lrkd_rank, (a.lrkd_alpha, a.lrkd_beta, a.lrkd_gamma), weight=0.1)
 
+    def parity(self):
+        """The loss depends on the (arbitrary) sign of every singular vector: the oracle's SVD columns are
+        sign-aligned to the basis the kernel returns before the KD term is compared (fp64 oracle: LAPACK fp32 is itself
+        only ~1e-4 accurate in the vectors of a 6 272 x 384 Gaussian matrix)."""
+        from oracle import losses as O
+        from deltakd_b200 import functional as Fn, heads as H
+        Bc = min(self.cpu_B or self.B, self.B)
+        hs = self.slice_host(self.host_sets(1, B=self.B)[0], Bc)
+        ds = self.to_device(hs)
+        a = self.args
+        coef = (a.lrkd_alpha, a.lrkd_beta, a.lrkd_gamma)
+        basis = {}
+        got = float(Fn.lrkd_layers_loss([ds["s"][0], ds["s"][1], ds["s"][11]], [ds["t"][0], ds["t"][1], ds["t"][11]],
+                                        list(self.student.align), a.lrkd_rank, coef, basis_out=basis).item())
+        heads = {k: v.detach().double().cpu() for k, v in H.head_tensors(self.student).items()}
+        s64 = [None if x is None else x.double() for x in hs["s"]]
+        t64 = [None if x is None else x.double() for x in hs["t"]]
+        signs = []
+        for j, ti in enumerate((0, 1, 11)):
+            _, V, _ = O.lrkd_targets(t64[ti][:, 2:], a.lrkd_rank)
+            signs.append(torch.sign((basis["V"][j].double().cpu().t() * V).sum(0)))
+        want = float(O.lrkd(s64, t64, heads, a.lrkd_rank, coef, signs=signs).item())
+        rel = abs(got - want) / max(abs(want), 1e-30)
+        return {"batch": Bc, "loss": got, "oracle": want, "rel_err": rel, "rtol": self.parity_rtol, "ok": rel <= self.parity_rtol,
+                "note": "KD term, oracle SVD columns sign-aligned to the kernel's basis"}
+
 
 class SaliencyMGD(MGD):
     """configs[3] (saliency variant): saliency-MGD method 1 (self-attention diagonal), ratio 0.5, B=512."""
@@ -497,6 +579,7 @@ class DeiTKDStep(Workload):
         ys = torch.softmax(torch.randn(2, 1000, device=self.device), dim=-1)
         self.opt = None
         self._graph = None
+        self._dry = (xs, ys)
         ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         # Under torchrun the whole-step graph (NCCL all-reduce inside) is used when this workload is the one selected with
         # --workload (verified at 2 and 8 GPUs); as one of several "extras" in a multi-rank process it runs eagerly —
@@ -508,7 +591,7 @@ class DeiTKDStep(Workload):
             side.wait_stream(torch.cuda.current_stream())
         # DDP under whole-step capture must be built (and warmed up) on a side stream; the eager path stays on the current one
         with (torch.cuda.stream(side) if use_graph else contextlib.nullcontext()):
-            self._eager_step((xs, ys), optimize=False)
+            self._dry_loss = self._eager_step((xs, ys), optimize=False).detach().clone()
             for p_ in self.student.parameters():
                 if p_.grad is None:
                     p_.requires_grad_(False)
@@ -533,7 +616,7 @@ class DeiTKDStep(Workload):
             from deltakd_b200 import _lib
             g = torch.cuda.CUDAGraph()
             c0 = _lib.lib.dkd_launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):
                 self._sloss = self._eager_step((self._sx, self._sy), zero=False)
             self.launches_per_step = int(_lib.lib.dkd_launch_count() - c0)   # libdeltakd kernels inside one replay
             self._graph = g
@@ -544,6 +627,14 @@ class DeiTKDStep(Workload):
 
     def h2d_bytes(self):
         return self.bytes_per_set()
+
+    def extra_info(self):
+        import torch.distributed as dist
+        ws = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        nbytes = sum(p_.numel() * p_.element_size() for p_ in self.student.parameters() if p_.requires_grad)
+        return {"collective": (f"DDP gradient all-reduce over NCCL ({ws} ranks, {nbytes / 1e6:.1f} MB of fp32 gradients per step, default 25 MB "
+                               "buckets) inside the captured step" if ws > 1 else "none (single rank)"),
+                "grad_bytes_per_step": nbytes, "img_per_s_per_gpu": None}
 
     def _eager_step(self, ds, optimize=True, zero=True):
         from deltakd_b200 import forward_with_features
@@ -570,6 +661,27 @@ class DeiTKDStep(Workload):
         return self._sloss
 
     op_only = step
+
+    parity_rtol = 3e-2   # bf16 autocast student + bf16 teacher on the GPU vs the fp32 models on the CPU
+
+    def parity(self):
+        """The 2-image dry-run step of setup() (same weights: both models are built under manual_seed(0)) against the fp32
+        CPU models + oracle loss on the same images."""
+        from oracle import losses as O
+        from deltakd_b200 import heads as H, features
+        xs, ys = (t.detach().float().cpu() for t in self._dry)
+        args, teacher, student, _, _ = self._build(torch.device("cpu"))
+        with torch.no_grad():
+            if self.kind in ("soft", "hard"):
+                t_logits, t_feats = teacher(xs), None
+                out, s_feats = student(xs), None
+            else:
+                t_logits, t_feats = features.forward_with_features(teacher, xs)
+                out, s_feats = features.forward_with_features(student, xs)
+            want = float(O.distillation_loss(self.kind, out, ys, t_logits, s_feats, t_feats, H.head_tensors(student), args, 0.1, 3.0).item())
+        got = float(self._dry_loss.item())
+        rel = abs(got - want) / max(abs(want), 1e-30)
+        return {"batch": int(xs.shape[0]), "loss": got, "oracle": want, "rel_err": rel, "rtol": self.parity_rtol, "ok": rel <= self.parity_rtol}
 
     def cpu_prepare(self, hs):
         return hs
@@ -624,8 +736,14 @@ class DeiTKDStepCurKD(DeiTKDStep):
 
 
 HEADLINE = LogitKD
-EXTRAS = (DeiTKDStep, DeiTKDStepCurKD, LogitKDLargeBatch, CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16, SaliencyMGD, LRKD, WassL1, WassSinkhorn)
+EXTRAS = (DeiTKDStep, DeiTKDStepCurKD, LogitKDf32, LogitKDf32B8, LogitKDLargeBatch, CurKDEarly, CurKDMid, CurKDEarlyBf16, MGD, MGDBf16,
+          SaliencyMGD, LRKD, WassL1, WassSinkhorn)
 WORKLOADS = {w.name: w for w in (HEADLINE,) + EXTRAS}
+# Under torchrun (N > 1) the line also carries the workloads whose step contains a collective — the end-to-end DeiT-Tiny KD
+# step with DDP's gradient all-reduce (~34 MB, reference tools/train.py:308) inside the captured step — and BASELINE
+# configs[4]: LRKD / WassKD at a GLOBAL batch of 1024 split data-parallel (B_loc = 1024 / N, no data-path collective).
+CFG5_GLOBAL_BATCH = 1024
+MULTI_RANK_EXTRAS = (DeiTKDStep, DeiTKDStepCurKD, LRKD, WassL1, WassSinkhorn)
 
 
 # ----------------------------------------------------------------------------- measurement
@@ -670,6 +788,22 @@ def run_reference(args, w_cls):
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_ncu_op(w_cls):
+    """One call of the fused op between cudaProfilerStart / Stop (inputs: set 0, after 2 warm-up calls)."""
+    torch.cuda.set_device(0)
+    w = w_cls(torch.device("cuda", 0), 0)
+    w.setup()
+    ds = w.to_device(w.host_sets(1)[0])
+    for _ in range(2):
+        w.op_only(ds)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    w.op_only(ds)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    print(json.dumps({"ncu_op": w.name}))
+
+
 def _graph_of(fn, reps):
     """Capture `reps` calls of fn() into one CUDA graph (after a side-stream warm-up call)."""
     side = torch.cuda.Stream()
@@ -679,7 +813,7 @@ def _graph_of(fn, reps):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=side):   # capture on the warm-up stream: the op scratch cached per stream is reused
         last = None
         for i in range(reps):
             last = fn(i)
@@ -688,22 +822,45 @@ def _graph_of(fn, reps):
     return g, last
 
 
-def _timed_replay(g, barrier):
-    barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ROUNDS = 11   # each round times EXACTLY K steps between barrier + synchronize; ms_per_step is the median round
+
+
+def _timed_replay(g, barrier, allmax=None, rounds=1):
+    """`rounds` timed replays of a K-step graph, each bracketed by barrier + torch.cuda.synchronize on both sides and
+    timed with CUDA events on the replay stream; per round the MAX over ranks is taken, then the median over rounds
+    (a single 20-step region of a 7 us step is 0.15 ms: one scheduling hiccup on one of 8 ranks moves it by 10 %).
+    Returns (ms of the median round, (wall t0, t1))."""
+    times = []
     t0 = time.time()
-    e0.record()
-    g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    return e0.elapsed_time(e1), (t0, time.time())
+    for _ in range(rounds):
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+    if allmax is not None:
+        times = allmax(times)
+    times.sort()
+    return times[len(times) // 2], (t0, time.time())
 
 
 def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_cpu: bool):
     from deltakd_b200 import _lib
     w.setup()
+    # ---- parity gate (rank 0 computes, every rank learns the verdict): nothing is timed unless the loss matches the oracle
+    par = None
+    if w.rank == 0 and os.environ.get("DKD_BENCH_PARITY", "1") != "0":
+        try:
+            par = w.parity()
+        except Exception as e:   # a crash of the check is a failed check
+            par = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+    bad = allmax([0.0 if (par is None or par["ok"]) else 1.0])[0]
+    if bad:
+        raise AssertionError(f"{w.name}: loss does not match the CPU oracle: {par}")
     nsets = w.nsets()
     host = w.host_sets(nsets)
     dsets = [w.to_device(h) for h in host]
@@ -718,30 +875,35 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
     if getattr(w, "graphable", True):
         graph, last = _graph_of(lambda i: w.step(dsets[(W + i) % nsets]), K)
         launches = (_lib.lib.dkd_launch_count() - c0) * K // (K + 1)   # the capture pass ran fn K+1 times
-        ms, win = _timed_replay(graph, barrier)
+        rounds = ROUNDS if K * 1.0 < 2000 else 1
+        ms, win = _timed_replay(graph, barrier, allmax, rounds)
         windows.append(win)
         loss_val = float(last.item())
         del graph
 
         # ---- the fused loss op alone (C-ABI call without the autograd rescale), same rotation, own graph
         kg, _ = _graph_of(lambda i: w.op_only(dsets[(W + i) % nsets]), K)
-        k_ms, win = _timed_replay(kg, barrier)
+        k_ms, win = _timed_replay(kg, barrier, None, min(rounds, 5))
         windows.append(win)
         k_ms /= K
         del kg
-    else:   # eager: K steps between two events (the step holds an optimizer and, multi-GPU, DDP's all-reduce)
-        barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    else:   # K whole steps between two events (the step holds an optimizer and, multi-GPU, DDP's all-reduce); 3 rounds, median
+        rounds_ms = []
         t0 = time.time()
-        e0.record()
-        for i in range(K):
-            last = w.step(dsets[(W + i) % nsets])
-        e1.record()
-        torch.cuda.synchronize()
-        barrier()
+        for _ in range(3):
+            barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                last = w.step(dsets[(W + i) % nsets])
+            e1.record()
+            torch.cuda.synchronize()
+            barrier()
+            rounds_ms.append(e0.elapsed_time(e1))
         windows.append((t0, time.time()))
-        ms = e0.elapsed_time(e1)
+        rounds_ms = sorted(allmax(rounds_ms))
+        ms = rounds_ms[1]
         launches = _lib.lib.dkd_launch_count() - c0
         if getattr(w, "_graph", None) is not None:   # replays do not pass through the library's host-side counter
             launches = w.launches_per_step * K
@@ -761,8 +923,7 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
     e3.record()
     torch.cuda.synchronize()
     windows.append((t0, time.time()))
-    ms_e2e = e2.elapsed_time(e3)
-    ms, ms_e2e = allmax([ms, ms_e2e])
+    ms_e2e = allmax([e2.elapsed_time(e3)])[0]
 
     if w.bound == "hbm":
         ach, peak, unit, alg = w.algorithmic_bytes() / (k_ms * 1e-3) / 1e9, pk["hbm"], "GB/s", w.algorithmic_bytes()
@@ -770,15 +931,15 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
         ach, peak, unit, alg = w.algorithmic_flops() / (k_ms * 1e-3) / 1e12, pk["bf16_sus"], "TFLOP/s", w.algorithmic_flops()
     res = {
         "workload": w.name, "value": world * w.B * K / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / K, "steps": K,
-        "dtype": w.dtype, "batch_per_gpu": w.B, "loss": loss_val,
+        "dtype": w.dtype, "batch_per_gpu": w.B, "loss": loss_val, "parity": par,
+        "rounds": "median of %d rounds of K steps, max over ranks per round" % (ROUNDS if getattr(w, "graphable", True) else 3),
         "l2": (f"{nsets} rotating input sets ({nsets * w.bytes_per_set() / 2**20:.0f} MiB > 126 MiB L2)" if nsets > 1
                else f"one input set of {w.bytes_per_set() / 2**20:.0f} MiB (> 126 MiB L2)"),
         "e2e": {"value": world * w.B * K / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": w.h2d_bytes(),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
         "roofline": {"bound": w.bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                     "traffic": NCU_TRAFFIC.get(w.name, (None, None, None))[0], "traffic_source": (
-                         f"ncu dram bytes, {NCU_TRAFFIC[w.name][1]} ({NCU_TRAFFIC[w.name][2]})" if w.name in NCU_TRAFFIC else None),
+                     "traffic": NCU_TRAFFIC.get(w.name, {}).get("bytes"), "traffic_source": NCU_TRAFFIC.get(w.name, {}).get("source"),
                      "kernel": w.dominant, "kernel_us": k_ms * 1e3, "peak_source": pk["src"],
                      ("algorithmic_bytes" if w.bound == "hbm" else "algorithmic_flops"): alg},
     }
@@ -789,6 +950,9 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
         res["roofline"]["algorithmic_flops"] = w.algorithmic_flops()
     if hasattr(w, "extra_roofline"):
         res["roofline"].update(w.extra_roofline(k_ms))
+    if hasattr(w, "extra_info"):
+        res.update(w.extra_info())
+        res["img_per_s_per_gpu"] = w.B * K / (ms * 1e-3)
     if with_cpu:
         res["cpu_baseline"] = cpu_baseline(w, budget_s=12.0 if isinstance(w, LogitKD) else 6.0)
     del dsets, host
@@ -806,12 +970,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only")
     ap.add_argument("--extras", action="store_true", help="also run the other workloads under torchrun (default: single-GPU runs only)")
+    ap.add_argument("--ncu-op", action="store_true",
+                    help="profiling helper: warm up, then run ONE call of the workload's fused op inside cudaProfilerStart/Stop "
+                         "(use with `ncu --profile-from-start off`; tools/ncu_traffic.py turns the CSV into profiles/ncu_traffic.json)")
     args = ap.parse_args()
     w_cls = WORKLOADS[args.workload]
     if args.steps is None:
         args.steps = w_cls.default_steps
     if args.impl == "reference":
         return run_reference(args, w_cls)
+    if args.ncu_op:
+        return run_ncu_op(w_cls)
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -845,12 +1014,17 @@ def main():
     # The other configs are reported beside the headline on single-GPU runs; a multi-rank run measures the selected
     # workload only unless --extras is given (keeps the 1 -> 8 scaling runs short; per-workload multi-GPU lines are
     # taken with --workload, see profiles/).
-    if not args.no_extras and w_cls is HEADLINE and (world == 1 or args.extras):
-        for cls in EXTRAS:
+    if not args.no_extras and w_cls is HEADLINE:
+        todo = EXTRAS if (world == 1 or args.extras) else MULTI_RANK_EXTRAS
+        for cls in todo:
             try:
-                wl = cls(dev, rank)
-                wl.allow_ddp_graph = False
+                if world > 1 and issubclass(cls, FeatureKD) and cls in (LRKD, WassL1, WassSinkhorn):
+                    wl = cls(dev, rank, B=CFG5_GLOBAL_BATCH // world)
+                else:
+                    wl = cls(dev, rank)
                 r, win = measure(wl, min(args.steps, cls.default_steps), W, world, barrier, allmax, pk, with_cpu)
+                if world > 1 and isinstance(wl, FeatureKD):
+                    r["global_batch"] = wl.B * world
             except Exception as e:  # one failing extra must not cost the headline line; it is reported, not hidden
                 r, win = {"workload": cls.name, "error": f"{type(e).__name__}: {e}"[:400]}, []
                 torch.cuda.synchronize()
@@ -867,7 +1041,8 @@ def main():
             "config": {"workload": head["workload"], "batch_per_gpu": head["batch_per_gpu"],
                        "timing": head.get("timing", "CUDA-graph replay of K steps, CUDA events, max over ranks"), "l2": head["l2"],
                        "teacher": ("frozen DeiT-Small teacher forward inside the step" if "deit" in head["workload"]
-                                   else "teacher outputs replayed (inputs of the loss path)"), "loss": head["loss"]},
+                                   else "teacher outputs replayed (inputs of the loss path)"), "loss": head["loss"],
+                       "parity": head.get("parity"), "rounds": head.get("rounds")},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": clocks,
         }
         if "cpu_baseline" in head:

@@ -37,6 +37,7 @@ SIGNATURES = {
     "dkd_scale_if_not_one": (_i, [_p, _i64, _p, _i64, _i, _p, _p]),
     "dkd_align_mse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_masked_generation_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
+    "dkd_masked_generation_hidden_offset": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_masked_generation_fwdbwd": (_i, [_p] * 10 + [_i64, _i, _i, _i, _i, _i, _i, _i, _i, _f] + [_p] * 10 + [_sz, _p]),
     "dkd_align_nmse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "dkd_align_nmse_fwdbwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),

@@ -121,6 +121,11 @@ size_t dkd_masked_generation_workspace_bytes(int64_t B, int n_tok, int Ds, int D
   return dkd::carve(nullptr, B * n_tok, Ds, Dt, precision == DKD_PREC_BF16X3 ? 2 : 1).bytes;
 }
 
+size_t dkd_masked_generation_hidden_offset(int64_t B, int n_tok, int Ds, int Dt, int precision) {
+  dkd::Workspace w = dkd::carve(nullptr, B * n_tok, Ds, Dt, precision == DKD_PREC_BF16X3 ? 2 : 1);
+  return (size_t)(reinterpret_cast<char*>(w.H) - static_cast<char*>(nullptr));
+}
+
 int dkd_masked_generation_fwdbwd(const void* s, const void* t, const float* mask, const float* W_align, const float* b_align,
                                  const float* mask_token, const float* conv1_w, const float* conv1_b, const float* conv2_w,
                                  const float* conv2_b, int64_t B, int Ts, int s_off, int Tt, int t_off, int Ds, int Dt, int dtype,

@@ -39,19 +39,37 @@ def _dtype_code(t: torch.Tensor) -> int:
     try:
         return _DT[t.dtype]
     except KeyError:
-        raise TypeError(f"unsupported dtype {t.dtype}: deltakd_b200 takes float32 or bfloat16") from None
+        raise TypeError(f"unsupported dtype {t.dtype}: the kernels take float32 or bfloat16 storage "
+                        "(float16 is upcast at the Python boundary; use autocast(dtype=torch.bfloat16) for a "
+                        "half-width path)") from None
 
 
-# zero-initialised scratch, cached per (device, tag, size); kernels leave their counters reset
+def _f16_up(t):
+    """float16 activations (the reference trainer's `--amp` autocast default, tools/engine.py:24) are upcast to
+    float32 with an ordinary differentiable cast: autograd hands the gradient back in float16.  The kernels' half
+    width storage type is bfloat16; float16 -> float32 is exact, so nothing is lost."""
+    if t is not None and t.dtype == torch.float16:
+        return t.float()
+    return t
+
+
+def _f16_up_list(ts):
+    return [_f16_up(t) for t in ts]
+
+
+# Scratch arenas are cached per (device, STREAM, tag): two streams (or two threads on their own streams) running the
+# same op never share a ticket counter or an arena.  Within one stream the launches are ordered, so reuse is safe.
+# zero-initialised variant: kernels leave their counters reset
 _WS: dict = {}
 
 
 def _workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
-    key = (device.index, tag)
+    key = (device.index, _stream(), tag)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1024), dtype=torch.uint8, device=device)
-        _WS[key] = ws
+        if not torch.cuda.is_current_stream_capturing():   # memory of a graph's private pool must not outlive the graph
+            _WS[key] = ws
     return ws
 
 
@@ -78,6 +96,22 @@ def _rescale_(grad_out: torch.Tensor, *grads):
         if rc:
             _lib.check(rc, "dkd_scale_if_not_one")
     return grads
+
+
+def _take_grads(ctx):
+    """Gradients precomputed by the fused forward launch.  They are handed to autograd ONCE and rescaled in place, so a
+    second backward through the same node (retain_graph=True, a loss reused in two graphs) is refused loudly instead of
+    returning twice-scaled or missing gradients.  Re-run the forward for a second backward."""
+    grads = ctx.grads
+    if grads is None:
+        raise RuntimeError("deltakd_b200: this loss was already backpropagated; the fused forward+backward kernels hold "
+                           "their gradients for a single backward pass (call the criterion again instead of "
+                           "retain_graph=True)")
+    ctx.grads = None
+    return grads
+
+
+_once = torch.autograd.function.once_differentiable
 
 
 # --------------------------------------------------------------------------- logit losses
@@ -123,9 +157,9 @@ class _LogitKD(torch.autograd.Function):
         return loss3[0]
 
     @staticmethod
+    @_once
     def backward(ctx, grad_total):
-        g0, g1 = ctx.grads
-        ctx.grads = None
+        g0, g1 = _take_grads(ctx)
         return _rescale_(grad_total, g0, g1) + (None,) * 8
 
 
@@ -138,6 +172,9 @@ def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, 
     Returns the 0-dim fp32 total `base*(1-alpha) + kd*alpha` (or base alone for "none").
     """
     kk = {"none": 0, "soft": 1, "hard": 2}[kd_kind]
+    outputs, outputs_kd, teacher_logits = _f16_up(outputs), _f16_up(outputs_kd), _f16_up(teacher_logits)
+    if labels is not None and labels.dtype == torch.float16:
+        labels = labels.float()
     ref = outputs if outputs is not None else outputs_kd
     _require_cuda(outputs, outputs_kd, teacher_logits, labels)
     if ref.dim() != 2:
@@ -197,12 +234,13 @@ def _precision_for(t: torch.Tensor) -> int:
 
 
 def _scratch(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
-    """Uninitialised, 1024-byte aligned scratch cached per (device, tag)."""
-    key = (device.index, "scratch:" + tag)
+    """Uninitialised, 1024-byte aligned scratch cached per (device, stream, tag)."""
+    key = (device.index, _stream(), "scratch:" + tag)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes + 1024:
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-        _WS[key] = ws
+        if not torch.cuda.is_current_stream_capturing():
+            _WS[key] = ws
     off = (-ws.data_ptr()) % 1024
     return ws[off:off + nbytes]
 
@@ -244,10 +282,10 @@ class _AlignMseLayers(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_once
     def backward(ctx, grad_out):
         n = ctx.n_layers
-        grads = ctx.grads
-        ctx.grads = None
+        grads = _take_grads(ctx)
         flat = [g for trip in grads for g in trip]
         _rescale_(grad_out, *flat)
         gs = [g[0] for g in grads]
@@ -256,12 +294,27 @@ class _AlignMseLayers(torch.autograd.Function):
         return (None, None, None, None, None, *gs, *([None] * n), *gw, *gb)
 
 
-def _check_feature_pair(s, t, s_off, t_off):
+SUPPORTED_WIDTHS = (192, 384)     # student -> teacher embedding widths the tcgen05 tile configurations are built for
+SUPPORTED_GRID_TOKENS = 196       # 14 x 14 patch grid (224-px inputs, patch 16) for the generator conv / Sinkhorn kernels
+
+
+def _check_feature_pair(s, t, s_off, t_off, op: str = "feature loss", grid_tokens: bool = False):
+    """Validates one (student, teacher) feature pair and states the supported model matrix in the error: the feature
+    kernels are compiled for DeiT-Tiny -> DeiT-Small widths (192 -> 384), which is what all 19 exp/*.sh scripts of the
+    reference use; other timm pairs (e.g. a 768-wide teacher, 384-px inputs) are rejected here, at the first call,
+    instead of failing deep inside a launch."""
     _require_cuda(s, t)
     if s.dim() != 3 or t.dim() != 3 or s.shape[0] != t.shape[0]:
         raise ValueError(f"features must be [B, tokens, dim]; got {tuple(s.shape)} and {tuple(t.shape)}")
     if s.shape[1] - s_off != t.shape[1] - t_off:
         raise ValueError(f"patch-token counts differ: student {s.shape[1] - s_off} vs teacher {t.shape[1] - t_off}")
+    if (s.shape[2], t.shape[2]) != SUPPORTED_WIDTHS:
+        raise ValueError(f"deltakd_b200 {op}: built for student/teacher widths {SUPPORTED_WIDTHS[0]} -> {SUPPORTED_WIDTHS[1]} "
+                         f"(deit_tiny -> deit_small, the pair of every exp/*.sh script); got {s.shape[2]} -> {t.shape[2]}. "
+                         "See INTEGRATION.md 'Supported model matrix'.")
+    if grid_tokens and s.shape[1] - s_off != SUPPORTED_GRID_TOKENS:
+        raise ValueError(f"deltakd_b200 {op}: built for {SUPPORTED_GRID_TOKENS} patch tokens (14 x 14 grid: 224-px inputs, patch 16); "
+                         f"got {s.shape[1] - s_off}. See INTEGRATION.md 'Supported model matrix'.")
 
 
 def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 1, t_off: int = 2,
@@ -269,8 +322,8 @@ def align_mse_layers_loss(s_feats, t_feats, linears, scale: float, s_off: int = 
     """scale * sum_i sum((linears[i](s_feats[i][:, s_off:]) - t_feats[i][:, t_off:])**2), 0-dim fp32."""
     n = len(linears)
     s_list, t_list, w_list, b_list = [], [], [], []
-    for s, t, lin in zip(s_feats, t_feats, linears):
-        _check_feature_pair(s, t, s_off, t_off)
+    for s, t, lin in zip(_f16_up_list(s_feats), _f16_up_list(t_feats), linears):
+        _check_feature_pair(s, t, s_off, t_off, op=_entry, grid_tokens=_entry == "dkd_wass_sinkhorn")
         t = t.detach()
         if t.dtype != s.dtype:
             t = t.to(s.dtype)
@@ -312,12 +365,12 @@ def wass_sinkhorn_loss(s_feats, t_feats, linears, weight: float = 5.0, s_off: in
 # --------------------------------------------------------------------------- masked generation (MGD family)
 class _MaskedGeneration(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scale, s_off, t_off, t, mask, s, Wa, ba, mask_token, c1w, c1b, c2w, c2b):
+    def forward(ctx, scale, s_off, t_off, probe, t, mask, s, Wa, ba, mask_token, c1w, c1b, c2w, c2b):
         B, Ts, Ds = s.shape
         _, Tt, Dt = t.shape
         dev = s.device
         prec = _precision_for(s)
-        need = ctx.needs_input_grad[5:]
+        need = ctx.needs_input_grad[6:]
         g_s = torch.empty_like(s) if need[0] else None
         outs = [g_s]
         for flag, ref in zip(need[1:], (Wa, ba, mask_token, c1w, c1b, c2w, c2b)):
@@ -329,24 +382,32 @@ class _MaskedGeneration(torch.autograd.Function):
         _lib.call("dkd_masked_generation_fwdbwd", _ptr(s), _ptr(t), _ptr(mask), _ptr(Wa), _ptr(ba), _ptr(mask_token),
                   _ptr(c1w), _ptr(c1b), _ptr(c2w), _ptr(c2b), B, Ts, s_off, Tt, t_off, Ds, Dt, _dtype_code(s), prec,
                   float(scale), *[_ptr(o) for o in outs], _ptr(loss), _ptr(ws), ws.numel(), _stream())
+        if probe is not None:   # verification hook: the hidden activations (ReLU gate) the backward pass used
+            P = 2 if prec == _lib.PREC_BF16X3 else 1
+            M = B * (Ts - s_off)
+            off = _lib.lib.dkd_masked_generation_hidden_offset(B, Ts - s_off, Ds, Dt, prec)
+            probe["hidden"] = ws[off:off + P * M * Dt * 2].view(torch.bfloat16).view(P, B, Ts - s_off, Dt).clone()
         ctx.grads = outs
         return loss
 
     @staticmethod
+    @_once
     def backward(ctx, grad_out):
-        outs = ctx.grads
-        ctx.grads = None
+        outs = _take_grads(ctx)
         _rescale_(grad_out, *outs)
-        return (None, None, None, None, None, *outs)
+        return (None, None, None, None, None, None, *outs)
 
 
 def masked_generation_loss(s_feat, t_feat, align, mask_token, generation, *, scale: float, mask=None,
-                           mask_ratio=None, noise=None, s_off: int = 1, t_off: int = 2):
+                           mask_ratio=None, noise=None, s_off: int = 1, t_off: int = 2, probe: dict | None = None):
     """scale * sum(mask * (generation(where(mask, mask_token, align(s[:, s_off:]))) - t[:, t_off:])**2).
 
     `mask` [B,196] (1 = masked) is used if given; otherwise it is drawn like the reference's
-    random_masking: noise = torch.rand(B, 196, device) (misc.py:14) -> rank -> mask (dkd_mask_rank)."""
-    _check_feature_pair(s_feat, t_feat, s_off, t_off)
+    random_masking: noise = torch.rand(B, 196, device) (misc.py:14) -> rank -> mask (dkd_mask_rank).
+    `probe` (verification only): receives "mask" and "hidden" = the generator's post-ReLU activations as bf16 planes
+    [P, B, 196, Dt], i.e. the ReLU gate the fused backward used (tests compare gradients given that gate)."""
+    s_feat, t_feat = _f16_up(s_feat), _f16_up(t_feat)
+    _check_feature_pair(s_feat, t_feat, s_off, t_off, op="masked generation", grid_tokens=True)
     B = s_feat.shape[0]
     L = s_feat.shape[1] - s_off
     if mask is None:
@@ -360,7 +421,9 @@ def masked_generation_loss(s_feat, t_feat, align, mask_token, generation, *, sca
     if t.dtype != s_feat.dtype:
         t = t.to(s_feat.dtype)
     f32 = lambda x: None if x is None else (x if x.dtype == torch.float32 else x.float()).contiguous()
-    return _MaskedGeneration.apply(scale, s_off, t_off, t.contiguous(), mask, s_feat.contiguous(), f32(align.weight),
+    if probe is not None:
+        probe["mask"] = mask
+    return _MaskedGeneration.apply(scale, s_off, t_off, probe, t.contiguous(), mask, s_feat.contiguous(), f32(align.weight),
                                    f32(align.bias), f32(mask_token.reshape(-1)), f32(conv1.weight), f32(conv1.bias),
                                    f32(conv2.weight), f32(conv2.bias))
 
@@ -492,10 +555,10 @@ class _LrkdLayers(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_once
     def backward(ctx, grad_out):
         n = ctx.n_layers
-        gs, gw, gb = ctx.grads
-        ctx.grads = None
+        gs, gw, gb = _take_grads(ctx)
         _rescale_(grad_out, *gs, *gw, *gb)
         return (None,) * 6 + (*gs, *([None] * n), *gw, *gb)
 
@@ -507,8 +570,8 @@ def lrkd_layers_loss(s_feats, t_feats, linears, rank: int, coef, weight: float =
     `basis_out` (dict) receives V (list of [rank, Dt]), S (singular values) and the Jacobi sweep counts."""
     n = len(linears)
     s_list, t_list, w_list, b_list = [], [], [], []
-    for s, t, lin in zip(s_feats, t_feats, linears):
-        _check_feature_pair(s, t, s_off, t_off)
+    for s, t, lin in zip(_f16_up_list(s_feats), _f16_up_list(t_feats), linears):
+        _check_feature_pair(s, t, s_off, t_off, op="LRKD")
         if lin.weight.shape[0] != rank:
             raise ValueError(f"LRKD head projects to {lin.weight.shape[0]} dims but rank is {rank}")
         t = t.detach()

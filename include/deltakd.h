@@ -191,6 +191,11 @@ DKD_API int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* 
  *   conv*_w : fp32 [Dt, Dt, 3, 3] (PyTorch layout), conv*_b : fp32 [Dt]
  */
 DKD_API size_t dkd_masked_generation_workspace_bytes(int64_t B, int n_tok, int Ds, int Dt, int precision);
+/* Byte offset, inside the workspace, of the generator's hidden activations h = relu(conv1(x_m)) as bf16 planes
+ * [P][B*196][Dt] (P = 2 hi/lo planes for DKD_PREC_BF16X3, else 1).  They stay valid after dkd_masked_generation_fwdbwd
+ * returns: verification code reads the ReLU gate the backward pass used from them (h != 0), because the gradient of
+ * F.relu (models.py:150) is discontinuous at 0 and parity of the gradients is only defined given the same gate. */
+DKD_API size_t dkd_masked_generation_hidden_offset(int64_t B, int n_tok, int Ds, int Dt, int precision);
 DKD_API int dkd_masked_generation_fwdbwd(const void* s, const void* t, const float* mask, const float* W_align,
                                          const float* b_align, const float* mask_token, const float* conv1_w,
                                          const float* conv1_b, const float* conv2_w, const float* conv2_b, int64_t B,

@@ -1,0 +1,92 @@
+"""GPU: host-side contract of the autograd wrappers: float16 inputs under the reference trainer's
+autocast call, per-stream scratch, and a loud error on a second backward."""
+import pytest
+import torch
+
+from oracle import losses as O
+from oracle.util import rel_err
+from deltakd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_float16_logits_under_reference_autocast():
+    """tools/engine.py:23-29 runs the student under torch.cuda.amp.autocast(enabled=True) (float16) and the criterion
+    outside it: float16 logits are upcast exactly at the boundary and the gradients come back as float16."""
+    from deltakd_b200 import DistillationLoss, call_base_loss
+    B, C = 16, 1000
+    z, zk, zt, y = synth.make_logits(B, C, 5)
+    lin = torch.nn.Linear(C, C).cuda()
+    x = z.cuda()
+    with torch.autocast("cuda", enabled=True):   # float16, as in the reference engine
+        out = lin(x)
+        out_kd = lin(zk.cuda())
+    assert out.dtype == torch.float16
+    args = synth.default_args()
+    teacher = synth.FeatureReplayModel(384)
+    teacher.set_outputs(zt.cuda(), None)
+    crit = DistillationLoss(call_base_loss(args), teacher, "soft", 0.1, 3.0)
+    loss = crit(torch.zeros(B, 3, 2, 2, device="cuda"), (out, out_kd), None, None, y.cuda(), args)
+    loss.backward()
+    assert lin.weight.grad is not None and torch.isfinite(lin.weight.grad).all()
+    o1 = out.detach().double().cpu().requires_grad_(True)
+    o2 = out_kd.detach().double().cpu().requires_grad_(True)
+    ref = O.distillation_loss("soft", (o1, o2), y.double(), zt.double(), None, None, {}, args, 0.1, 3.0)
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+
+
+def test_float16_features_are_accepted():
+    from deltakd_b200 import functional as Fn
+    s_feats, t_feats = synth.make_features(3, 9, layers=[0])
+    lin = torch.nn.Linear(192, 384).cuda()
+    s16 = s_feats[0].cuda().half().requires_grad_(True)
+    t16 = t_feats[0].cuda().half()
+    loss = Fn.align_mse_layers_loss([s16], [t16], [lin], 1e-4)
+    loss.backward()
+    assert s16.grad is not None and s16.grad.dtype == torch.float16
+    s64 = s16.detach().double().cpu().requires_grad_(True)
+    ref = (((s64[:, 1:] @ lin.weight.double().cpu().t() + lin.bias.double().cpu()) - t16.double().cpu()[:, 2:]) ** 2).sum() * 1e-4
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert rel_err(s16.grad.float(), s64.grad) < 2e-3   # the gradient is rounded to float16 on the way back
+
+
+def test_unsupported_widths_raise_clearly():
+    from deltakd_b200 import functional as Fn
+    s = torch.randn(2, 197, 384, device="cuda", requires_grad=True)
+    t = torch.randn(2, 198, 768, device="cuda")
+    with pytest.raises(ValueError, match="192 -> 384"):
+        Fn.align_mse_layers_loss([s], [t], [torch.nn.Linear(384, 768).cuda()], 1e-4)
+    s2 = torch.randn(2, 577, 192, device="cuda", requires_grad=True)   # 384-px inputs: 24 x 24 patches
+    t2 = torch.randn(2, 578, 384, device="cuda")
+    with pytest.raises(ValueError, match="196 patch tokens"):
+        Fn.wass_sinkhorn_loss([s2], [t2], [torch.nn.Linear(192, 384).cuda()])
+
+
+def test_second_backward_is_refused():
+    from deltakd_b200 import functional as Fn
+    z, zk, zt, y = (t.cuda() for t in synth.make_logits(8, 100, 3))
+    z.requires_grad_(True); zk.requires_grad_(True)
+    loss = Fn.logit_kd_loss(z, zk, zt, y, kd_kind="soft", alpha=0.1, tau=3.0)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already backpropagated"):
+        loss.backward()
+
+
+def test_two_streams_do_not_share_scratch():
+    """The same op on two streams at once: each stream has its own ticket counter / arenas (functional._WS is keyed by
+    stream), so both results equal the single-stream result."""
+    from deltakd_b200 import functional as Fn
+    z, zk, zt, y = (t.cuda() for t in synth.make_logits(256, 1000, 11))
+    want = Fn.logit_kd_loss(z, zk, zt, y, kd_kind="soft", alpha=0.1, tau=3.0).item()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(20):
+        for st in (s1, s2):
+            with torch.cuda.stream(st):
+                outs.append(Fn.logit_kd_loss(z, zk, zt, y, kd_kind="soft", alpha=0.1, tau=3.0))
+    torch.cuda.synchronize()
+    assert all(o.item() == want for o in outs)
+    keys = [k for k in Fn._WS if k[2] == "logit_kd"]
+    assert len({k[1] for k in keys}) >= 3   # default stream + the two side streams
