@@ -17,8 +17,13 @@ namespace dkd {
 
 // PLANES_ = 2: a stage holds both bf16 planes of the A and B blocks and the three bf16x3 products are issued from it
 // (each operand byte is fetched once instead of 1.5 times); the caller passes nterms = 3.
-template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64, bool A_KMAJOR_ = false, int PLANES_ = 1>
+// CLUSTER_ > 1: clusters of CLUSTER_ CTAs work on items that share the B operand (same contraction rows, same B columns,
+// different A column tile): each CTA fetches 1/CLUSTER_ of every B block and multicasts it to the cluster (Loader::issue_cluster).
+template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ = 64, bool A_KMAJOR_ = false, int PLANES_ = 1,
+          int CLUSTER_ = 1>
 struct GemmNtCfg {
+  static constexpr int CLUSTER = CLUSTER_;
+  static_assert(CLUSTER_ == 1 || PLANES_ == 1, "the cluster form streams one plane pair per stage");
   static constexpr int PLANES = PLANES_;
   static constexpr bool A_KMAJOR = A_KMAJOR_;       // A tile is [128 rows x 64 k] K-major (one box) instead of two MN-major boxes
   static constexpr int NA = 128;                      // UMMA M
@@ -82,9 +87,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = Loader::num_items(p.ld);
+  // cluster form: the CTAs of a cluster take the same item (the loader maps the rank to the A column tile)
+  const int crank = Cfg::CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  const int item0 = (int)blockIdx.x / Cfg::CLUSTER, item_step = (int)gridDim.x / Cfg::CLUSTER;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << Cfg::CLUSTER) - 1u);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::CLUSTER); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 4);
     fence_barrier_init();
@@ -93,15 +102,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (Cfg::CLUSTER > 1) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         typename Loader::Item it;
-        Loader::decode(p.ld, item, it);
+        if constexpr (Cfg::CLUSTER > 1) Loader::decode_cluster(p.ld, item, crank, it);
+        else Loader::decode(p.ld, item, it);
         if constexpr (Cfg::PLANES == 2) {
           for (int rb = it.rb0; rb < it.rb1; ++rb) {
             mbar_wait(&empty[s], ph ^ 1);
@@ -115,7 +126,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
             for (int rb = it.rb0; rb < it.rb1; ++rb) {
               mbar_wait(&empty[s], ph ^ 1);
               mbar_expect_tx(&full[s], Loader::TX_BYTES);
-              Loader::issue(p.ld, it, term, p.nterms, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
+              if constexpr (Cfg::CLUSTER > 1)
+                Loader::issue_cluster(p.ld, it, term, p.nterms, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], crank);
+              else
+                Loader::issue(p.ld, it, term, p.nterms, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
               if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
             }
           }
@@ -128,9 +142,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
       constexpr uint32_t idesc0 = make_idesc_bf16(128, Cfg::N0, a_major, MAJOR_MN);
       constexpr uint32_t idesc1 = make_idesc_bf16(128, Cfg::N1 > 0 ? Cfg::N1 : 16, a_major, MAJOR_MN);
       int s = 0; uint32_t ph = 0; uint32_t aph = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         typename Loader::Item it;
-        Loader::decode(p.ld, item, it);
+        if constexpr (Cfg::CLUSTER > 1) Loader::decode_cluster(p.ld, item, crank, it);
+        else Loader::decode(p.ld, item, it);
         const int nk = (it.rb1 - it.rb0) * (Cfg::PLANES == 2 ? 1 : p.nterms);
         if (nk <= 0) continue;  // (hosts never create empty splits)
         mbar_wait(acc_empty, aph ^ 1);
@@ -154,7 +169,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
                           idesc1, (kit | term | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty[s]);
+          if constexpr (Cfg::CLUSTER > 1) umma_commit_mc(&empty[s], kClusterMask);
+          else umma_commit(&empty[s]);
           if (kit == nk - 1) umma_commit(acc_full);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
@@ -165,9 +181,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     uint32_t aph = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = item0; item < num_items; item += item_step) {
       typename Loader::Item it;
-      Loader::decode(p.ld, item, it);
+      if constexpr (Cfg::CLUSTER > 1) Loader::decode_cluster(p.ld, item, crank, it);
+      else Loader::decode(p.ld, item, it);
       if (it.rb1 <= it.rb0) continue;
       mbar_wait(acc_full, aph);
       tc_fence_after();
@@ -209,10 +226,51 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (Cfg::CLUSTER > 1) cluster_sync();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+// host: launch, as clusters of Cfg::CLUSTER CTAs when asked (`grid` = CTAs, a multiple of the cluster size)
+template <class Cfg, class Loader>
+inline void launch_gemm_nt(const GemmNtParamsT<Cfg, Loader>& p, int grid, cudaStream_t st) {
+  auto kern = gemm_nt_kernel<Cfg, Loader>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if constexpr (Cfg::CLUSTER > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = Cfg::CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p);
+  } else {
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+  }
+}
+
+// host: number of row splits in [lo, hi] that fills whole waves best: maximises items / (ceil(items / slots) * slots)
+inline int nt_best_splits(int combos, int slots, int total_row_blocks, int lo, int hi) {
+  int best = lo;
+  double best_eff = -1.0;
+  for (int sp = lo; sp <= hi && sp <= total_row_blocks; ++sp) {
+    const int per = (total_row_blocks + sp - 1) / sp;
+    const int real = (total_row_blocks + per - 1) / per;         // splits that exist after rounding
+    const long items = (long)combos * real;
+    const long waves = (items + slots - 1) / slots;
+    // ragged last split costs a full `per`: weigh by the work actually done
+    const double eff = (double)combos * total_row_blocks / ((double)waves * slots * per);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+  }
+  return best;
 }
 
 struct NtItem {

@@ -24,8 +24,13 @@ namespace dkd {
 // EPI_WARPS_ = 8: two epilogue warps per TMEM lane quadrant (two per scheduler); group g of the two takes the 32-column
 // chunks g, g+2, ... of a tile.  The epilogue is a chain of TMEM reads, DRAM round trips and stores; with a single
 // epilogue warp per scheduler nothing hides those latencies.  Policies used this way take (group, groups) in tile().
-template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128, int PLANES_ = 1, int EPI_WARPS_ = 4>
+// CLUSTER_ > 1: the kernel runs as thread-block clusters of CLUSTER_ CTAs that walk their tiles in lockstep; loaders that
+// support it fetch the operand every CTA of the cluster needs (the weights of a convolution) ONCE per cluster and multicast
+// it — the L2 -> SM operand feed (~55 B/clk/SM measured) is what bounds the K = 3456 convolution GEMMs, not the tensor pipe.
+template <int BN_, int NI_, int STAGES_, int ACC_, int TILE_M_ = 128, int PLANES_ = 1, int EPI_WARPS_ = 4, int CLUSTER_ = 1>
 struct GemmCfg {
+  static constexpr int CLUSTER = CLUSTER_;
+  static_assert(CLUSTER_ >= 1 && CLUSTER_ <= 8, "portable cluster size");
   static constexpr int PLANES = PLANES_;
   static constexpr int EPI_WARPS = EPI_WARPS_;
   static constexpr int EPI_GROUPS = EPI_WARPS_ / 4;
@@ -76,9 +81,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int num_k = Loader::num_k_iters(p.ld);
+  // Clusters walk tiles in lockstep: every CTA of a cluster runs the same number of tile iterations (a CTA whose tile
+  // index is past the end runs a phantom tile: its loads are zero-filled, its epilogue stores nothing).
+  const int crank = Cfg::CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  const int tile0 = (int)blockIdx.x - crank;           // first tile of this CTA's cluster
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << Cfg::CLUSTER) - 1u);
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::CLUSTER); }
     for (int a = 0; a < Cfg::ACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], Cfg::EPI_WARPS); }
     fence_barrier_init();
     Loader::prefetch(p.ld);
@@ -86,6 +96,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (Cfg::CLUSTER > 1) cluster_sync();   // every CTA's barriers exist before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -93,12 +104,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int base = tile0; base < num_tiles; base += gridDim.x) {
+        const int tile = base + crank;
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         for (int kit = 0; kit < num_k; ++kit) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], Loader::TX_BYTES);
-          Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
+          if constexpr (Cfg::CLUSTER > 1) Loader::issue_cluster(p.ld, kit, mt, nt, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], crank);
+          else Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -109,7 +122,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
       constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, Cfg::N_INSTR, MAJOR_K, MAJOR_K);
       int s = 0; uint32_t ph = 0;
       int a = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int base = tile0; base < num_tiles; base += gridDim.x) {
         mbar_wait(&acc_empty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * Cfg::BN);
@@ -133,7 +146,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
               }
             }
           }
-          umma_commit(&empty[s]);                       // ring slot reusable once these MMAs retire
+          if constexpr (Cfg::CLUSTER > 1) umma_commit_mc(&empty[s], kClusterMask);   // ... in every CTA of the cluster
+          else umma_commit(&empty[s]);                  // ring slot reusable once these MMAs retire
           if (kit == num_k - 1) umma_commit(&acc_full[a]);  // accumulator complete
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
@@ -147,7 +161,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
     typename Epi::State st;
     Epi::init(p.ep, st);
     int a = 0; uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int base = tile0; base < num_tiles; base += gridDim.x) {
+      const int tile = base + crank;
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
@@ -164,9 +179,73 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (Cfg::CLUSTER > 1) cluster_sync();   // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// host: how many clusters of `cluster` CTAs (one CTA per SM: `smem` bytes, `threads`) can be resident at once.  Clusters
+// are placed inside one GPC, so this can be fewer than 148 / cluster; a persistent kernel must not launch more (a cluster
+// that starts only after another has finished ALL its tiles would double the makespan).  Cached per kernel.
+template <class Kern>
+inline int max_resident_clusters(Kern kern, int cluster, int threads, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(kNumSMs / cluster * cluster));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = kNumSMs / cluster; }
+  if (n > kNumSMs / cluster) n = kNumSMs / cluster;
+  return n;
+}
+
+// host: CTAs to launch for `tiles` tiles (whole clusters; phantom tiles cover the remainder)
+template <class Cfg, class Loader, class Epi>
+inline int gemm_tn_grid(int tiles) {
+  if constexpr (Cfg::CLUSTER > 1) {
+    auto kern = gemm_tn_kernel<Cfg, Loader, Epi>;
+    static const int resident = [&] {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+      return max_resident_clusters(kern, Cfg::CLUSTER, Cfg::THREADS, Cfg::SMEM);
+    }();
+    int clusters = (tiles + Cfg::CLUSTER - 1) / Cfg::CLUSTER;
+    if (clusters > resident) clusters = resident;
+    return clusters * Cfg::CLUSTER;
+  } else {
+    return tiles < kNumSMs ? tiles : kNumSMs;
+  }
+}
+
+// host: launch a gemm_tn kernel, as clusters of Cfg::CLUSTER CTAs when the configuration asks for them (grid from gemm_tn_grid)
+template <class Cfg, class Loader, class Epi>
+inline void launch_gemm_tn(const GemmParams<Loader, Epi>& p, int grid, cudaStream_t st) {
+  auto kern = gemm_tn_kernel<Cfg, Loader, Epi>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  if constexpr (Cfg::CLUSTER > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = Cfg::CLUSTER;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p);
+  } else {
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
   }
 }
 

@@ -7,6 +7,8 @@
 // both gradient rows are written in the same launch, and the last CTA to finish folds the per-row
 // partials in a fixed order (deterministic) into {total, base, kd}.
 // HBM-bound: algorithmic bytes = (reads + grad writes) * B * C * sizeof(elt); no tensor-core work.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dkd {
@@ -61,9 +63,13 @@ struct LogitKdParams {
 // modes are instantiated so that the per-element mode tests vanish from the unrolled inner loops.
 constexpr int kRuntimeMode = -2;
 constexpr float kL2e = 1.4426950408889634f;
-template <typename T, int VEC, int NV, int THREADS = kThreads, int LK = kRuntimeMode, int KK = kRuntimeMode>
+// gz_row / gzk_row: where this row's gradients go (global rows, or the ring stage of the streaming kernel; null = not
+// wanted).  PACK2: fp32-pair arithmetic in passes 2 and 3.
+template <typename T, int VEC, int NV, int THREADS = kThreads, int LK = kRuntimeMode, int KK = kRuntimeMode,
+          bool PACK2 = (THREADS == kThreads)>
 __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, const T* z, const T* zk, const T* zt, const T* y,
-                                          float* scratch, int* s_arg, float* s_argv) {
+                                          T* gz_row, T* gzk_row, float* scratch, int* s_arg, float* s_argv, float& base_out,
+                                          float& kd_out) {
   const int64_t C = p.C;
   const int label_kind = LK == kRuntimeMode ? p.label_kind : LK;
   const int kd_kind = KK == kRuntimeMode ? p.kd_kind : KK;
@@ -174,7 +180,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   // fewer instructions per row.  Measured A/B on one B200: the latency-chain case (B = 256, 4-warp CTAs) gains
   // 5.87 -> 5.71 us; the large-batch 2-warp variant is bound by bytes in flight, not by issue, and loses 3 %
   // (56.2 -> 58.0 us at B = 16 384) — so only the small-batch shape uses the packed forms.
-  constexpr bool PACKED = NV > 0 && VEC % 2 == 0 && THREADS == kThreads;
+  constexpr bool PACKED = NV > 0 && VEC % 2 == 0 && PACK2;
   float2 S2[4], T2[2];   // pair accumulators of s[0..3], t[0..1]
 #pragma unroll
   for (int k = 0; k < 4; ++k) S2[k] = make_float2(0.f, 0.f);
@@ -287,8 +293,8 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   const float k0 = (label_kind == 0 ? inv_s0 * t[0] : inv_s0) * wb;
   const float k1 = inv_s1 * wk, k2 = inv_s2 * wk;
   const float sm_wb = p.smoothing / Cf * wb, hot_wb = (1.f - p.smoothing) * wb;
-  T* gz = (p.gz && label_kind >= 0) ? reinterpret_cast<T*>(p.gz) + row * C : nullptr;
-  T* gzk = (p.gzk && kd_kind) ? reinterpret_cast<T*>(p.gzk) + row * C : nullptr;
+  T* gz = label_kind >= 0 ? gz_row : nullptr;
+  T* gzk = kd_kind ? gzk_row : nullptr;
   auto pass3 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
     const int64_t col = col_of(it);
     if (col < C) {
@@ -348,15 +354,14 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
     }
   }
 
-  if (tid == 0) {
-    p.row_base[row] = base_row;
-    p.row_kd[row] = kd_row;
-  }
+  base_out = base_row;   // valid in every thread (block-wide sums); the caller stores or accumulates them
+  kd_out = kd_row;
 }
 
 // Last CTA to finish folds the per-row partials in a fixed order (bit-reproducible) into {total, base, kd}.
+// `n_part`: number of partial sums in row_base / row_kd (one per row, or one per warp of the ring kernel)
 template <int THREADS = kThreads>
-__device__ __forceinline__ void logit_finalize(const LogitKdParams& p, float* scratch, bool* s_last) {
+__device__ __forceinline__ void logit_finalize(const LogitKdParams& p, float* scratch, bool* s_last, int64_t n_part) {
   const float Bf = (float)p.B, Cf = (float)p.C;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -368,7 +373,7 @@ __device__ __forceinline__ void logit_finalize(const LogitKdParams& p, float* sc
   __threadfence();
   float acc[2] = {0.f, 0.f};
   // fixed thread->row assignment and fixed tree => bit-reproducible
-  for (int64_t r = threadIdx.x; r < p.B; r += THREADS) {
+  for (int64_t r = threadIdx.x; r < n_part; r += THREADS) {
     acc[0] += __ldcg(p.row_base + r);
     acc[1] += __ldcg(p.row_kd + r);
   }
@@ -382,6 +387,30 @@ __device__ __forceinline__ void logit_finalize(const LogitKdParams& p, float* sc
     p.loss_out[1] = base;
     p.loss_out[2] = kd;
     *p.ticket = 0u;  // ready for the next call on this workspace
+  }
+}
+
+// fold by the first warp only (block size not known at compile time)
+__device__ __forceinline__ void logit_finalize_any(const LogitKdParams& p, float* scratch, bool* s_last, int64_t n_part) {
+  const float Bf = (float)p.B, Cf = (float)p.C;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(p.ticket, 1u);
+    *s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!*s_last || threadIdx.x >= 32) return;
+  __threadfence();
+  float a0 = 0.f, a1 = 0.f;
+  for (int64_t r = threadIdx.x; r < n_part; r += 32) { a0 += __ldcg(p.row_base + r); a1 += __ldcg(p.row_kd + r); }
+  a0 = warp_sum(a0); a1 = warp_sum(a1);
+  if (threadIdx.x == 0) {
+    const float base = a0 / Bf;
+    float kd = 0.f, total = base;
+    if (p.kd_kind == 1) { kd = a1 * p.tau * p.tau / (Bf * Cf); total = base * (1.f - p.alpha) + kd * p.alpha; }
+    else if (p.kd_kind == 2) { kd = a1 / Bf; total = base * (1.f - p.alpha) + kd * p.alpha; }
+    p.loss_out[0] = total; p.loss_out[1] = base; p.loss_out[2] = kd;
+    *p.ticket = 0u;
   }
 }
 
@@ -427,8 +456,151 @@ __global__ void __launch_bounds__(THREADS) logit_kd_kernel(LogitKdParams p) {
   const T* zk = p.kd_kind ? reinterpret_cast<const T*>(p.zk) + row * C : nullptr;
   const T* zt = p.kd_kind ? reinterpret_cast<const T*>(p.zt) + row * C : nullptr;
   const T* y = p.label_kind == 0 ? reinterpret_cast<const T*>(p.y) + row * C : nullptr;
-  logit_row<T, VEC, NV, THREADS, LK, KK>(p, row, z, zk, zt, y, scratch, s_arg, s_argv);
-  if (TICKET) logit_finalize<THREADS>(p, scratch, &s_last);
+  T* gz = p.gz ? reinterpret_cast<T*>(p.gz) + row * C : nullptr;
+  T* gzk = p.gzk ? reinterpret_cast<T*>(p.gzk) + row * C : nullptr;
+  float base_row, kd_row;
+  logit_row<T, VEC, NV, THREADS, LK, KK>(p, row, z, zk, zt, y, gz, gzk, scratch, s_arg, s_argv, base_row, kd_row);
+  if (threadIdx.x == 0) {
+    p.row_base[row] = base_row;
+    p.row_kd[row] = kd_row;
+  }
+  if (TICKET) logit_finalize<THREADS>(p, scratch, &s_last, p.B);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Large batches: persistent CTAs, ONE WARP PER ROW, rows streamed through a per-warp ring of shared-memory stages by
+// bulk copies (cp.async.bulk + mbarrier complete_tx) — no thread ever waits on a global load:
+//   lane 0   issues the 2-4 operand rows of row k+2 into the stage row k-1 has left,
+//   the warp waits on row k's mbarrier, reads the stage once into registers (the three passes of logit_row run on
+//            registers, warp shuffles only: no block barrier anywhere), writes both gradient rows back INTO the stage
+//            (over z and zk) and lane 0 sends them to HBM with bulk stores.
+// The one-CTA-per-row form keeps a row's loads in flight only for the first third of the CTA's life (two block
+// reductions sit between its load and store phases): 56 % of the HBM copy rate at B = 16 384; here every warp always
+// has 1-2 rows (8-16 KB) of bulk loads in flight and the stores drain asynchronously.
+constexpr int kRingStages = 3;
+constexpr int kRingMaxWarps = 8;
+constexpr int kRingSmemBudget = 224 * 1024;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void ring_bar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void ring_bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ring_bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) {   // a protocol bug traps instead of hanging the GPU
+      printf("dkd: logit ring wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+template <typename T, int VEC, int NV, int LK, int KK>
+__global__ void __launch_bounds__(32 * kRingMaxWarps, 1) logit_ring_kernel(LogitKdParams p, int row_stride /* bytes, multiple of 128 */) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  constexpr int NOPS = (LK >= 0 ? 1 : 0) + (LK == 0 ? 1 : 0) + (KK ? 2 : 0);
+  // stage layout: [z][zk][zt][y] (only the operands the mode reads); gradients overwrite z and zk
+  constexpr int O_Z = 0, O_ZK = (LK >= 0 ? 1 : 0), O_ZT = O_ZK + 1, O_Y = O_ZK + (KK ? 2 : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int64_t C = p.C;
+  const uint32_t row_bytes = (uint32_t)(C * sizeof(T));
+  const int stage_bytes = NOPS * row_stride;
+  uint8_t* wbase = ring_smem + (size_t)warp * kRingStages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_smem + (size_t)nw * kRingStages * stage_bytes) + warp * kRingStages;
+  const int64_t gw = (int64_t)blockIdx.x * nw + warp, GW = (int64_t)gridDim.x * nw;
+  const int64_t nrows = gw < p.B ? (p.B - gw + GW - 1) / GW : 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kRingStages; ++s) ring_bar_init(&bars[s]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const T* gZ = reinterpret_cast<const T*>(p.z);
+  const T* gZK = reinterpret_cast<const T*>(p.zk);
+  const T* gZT = reinterpret_cast<const T*>(p.zt);
+  const T* gY = reinterpret_cast<const T*>(p.y);
+  auto issue = [&](int64_t k) {   // lane 0 only
+    const int s = (int)(k % kRingStages);
+    const int64_t off = (gw + k * GW) * C;
+    uint8_t* st = wbase + (size_t)s * stage_bytes;
+    ring_bar_expect(&bars[s], NOPS * row_bytes);
+    if (LK >= 0) bulk_g2s(st + O_Z * row_stride, gZ + off, row_bytes, &bars[s]);
+    if (KK) {
+      bulk_g2s(st + O_ZK * row_stride, gZK + off, row_bytes, &bars[s]);
+      bulk_g2s(st + O_ZT * row_stride, gZT + off, row_bytes, &bars[s]);
+    }
+    if (LK == 0) bulk_g2s(st + O_Y * row_stride, gY + off, row_bytes, &bars[s]);
+  };
+  if (lane == 0) {
+    for (int64_t k = 0; k < kRingStages - 1 && k < nrows; ++k) issue(k);
+  }
+  float acc_base = 0.f, acc_kd = 0.f;
+  for (int64_t k = 0; k < nrows; ++k) {
+    const int s = (int)(k % kRingStages);
+    const uint32_t parity = (uint32_t)((k / kRingStages) & 1);
+    uint8_t* st = wbase + (size_t)s * stage_bytes;
+    const int64_t row = gw + k * GW;
+    ring_bar_wait(&bars[s], parity);
+    T* sz = reinterpret_cast<T*>(st + O_Z * row_stride);
+    T* szk = reinterpret_cast<T*>(st + O_ZK * row_stride);
+    const T* szt = reinterpret_cast<const T*>(st + O_ZT * row_stride);
+    const T* sy = reinterpret_cast<const T*>(st + O_Y * row_stride);
+    float base_row, kd_row;
+    logit_row<T, VEC, NV, 32, LK, KK, true>(p, row, LK >= 0 ? sz : nullptr, KK ? szk : nullptr, KK ? szt : nullptr, LK == 0 ? sy : nullptr,
+                                            (p.gz && LK >= 0) ? sz : nullptr, (p.gzk && KK) ? szk : nullptr, nullptr, nullptr, nullptr,
+                                            base_row, kd_row);
+    acc_base += base_row;   // this warp's rows, in row order: fixed for a given (B, grid)
+    acc_kd += kd_row;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the gradient rows (generic-proxy writes) -> visible to the bulk stores
+    __syncwarp();
+    if (lane == 0) {
+      const int64_t off = row * C;
+      if (p.gz && LK >= 0) bulk_s2g(reinterpret_cast<T*>(p.gz) + off, sz, row_bytes);
+      if (p.gzk && KK) bulk_s2g(reinterpret_cast<T*>(p.gzk) + off, szk, row_bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the stage of row k-1 is free once ITS stores have read shared memory (all but the newest group)
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      if (k + kRingStages - 1 < nrows) issue(k + kRingStages - 1);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA's shared memory goes away
+    if (gw < p.B) {              // one partial per warp that owns rows (the workspace holds B entries)
+      p.row_base[gw] = acc_base;
+      p.row_kd[gw] = acc_kd;
+    }
+  }
+  const int64_t n_part = GW < p.B ? GW : p.B;
+  // last CTA folds the GW per-warp partials in a fixed order: no second launch
+  __shared__ float scratch[2 * kRingMaxWarps];
+  __shared__ bool s_last;
+  __syncthreads();
+  if (blockDim.x == 32 * kRingMaxWarps) logit_finalize<32 * kRingMaxWarps>(p, scratch, &s_last, n_part);
+  else logit_finalize_any(p, scratch, &s_last, n_part);
 }
 
 // one (threads, ticket) shape; NV by row length; the six usual (label_kind, kd_kind) modes are compiled in
@@ -452,12 +624,50 @@ void launch_mode(const LogitKdParams& p, int64_t nchunk, dim3 grid, cudaStream_t
   launch_nv<T, VEC, THREADS, TICKET, kRuntimeMode, kRuntimeMode>(p, nchunk, grid, stream);
 }
 
+// streaming launch for one compiled (label_kind, kd_kind) mode; false when the mode / shape is not covered
+template <typename T, int VEC, int NV, int LK, int KK>
+int launch_ring_mode(const LogitKdParams& p, cudaStream_t stream) {
+  constexpr int NOPS = (LK >= 0 ? 1 : 0) + (LK == 0 ? 1 : 0) + (KK ? 2 : 0);
+  const int row_stride = (int)((p.C * (int64_t)sizeof(T) + 127) / 128 * 128);
+  int warps = kRingSmemBudget / (kRingStages * NOPS * row_stride);
+  if (warps > kRingMaxWarps) warps = kRingMaxWarps;
+  if (warps < 2) return 1;   // rows too long for the ring: caller falls back
+  const size_t smem = (size_t)warps * kRingStages * NOPS * row_stride + (size_t)warps * kRingStages * sizeof(uint64_t);
+  int64_t grid = (p.B + warps - 1) / warps;
+  if (grid > kNumSMs) grid = kNumSMs;
+  auto kern = logit_ring_kernel<T, VEC, NV, LK, KK>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(unsigned)grid, 32 * warps, smem, stream>>>(p, row_stride);
+  return 0;
+}
+template <typename T, int VEC, int NV>
+int launch_ring(const LogitKdParams& p, cudaStream_t stream) {
+  const int lk = p.label_kind, kk = p.kd_kind;
+  if (lk == 0 && kk == 1) return launch_ring_mode<T, VEC, NV, 0, 1>(p, stream);
+  if (lk == 1 && kk == 1) return launch_ring_mode<T, VEC, NV, 1, 1>(p, stream);
+  if (lk == 0 && kk == 2) return launch_ring_mode<T, VEC, NV, 0, 2>(p, stream);
+  if (lk == 1 && kk == 2) return launch_ring_mode<T, VEC, NV, 1, 2>(p, stream);
+  if (lk == 0 && kk == 0) return launch_ring_mode<T, VEC, NV, 0, 0>(p, stream);
+  if (lk == 1 && kk == 0) return launch_ring_mode<T, VEC, NV, 1, 0>(p, stream);
+  return 1;
+}
+bool ring_enabled() {
+  static const bool on = [] { const char* e = getenv("DKD_LOGIT_RING"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <typename T, int VEC>
 int launch_logit_kd(const LogitKdParams& p, cudaStream_t stream) {
   const int64_t per_chunk = (int64_t)kThreads * VEC;
   const int64_t nchunk = (p.C + per_chunk - 1) / per_chunk;
   dim3 grid((unsigned)p.B), block(kThreads);
   const int64_t nchunk64 = (p.C + 64 * VEC - 1) / (64 * VEC);
+  if constexpr (VEC * sizeof(T) == 16) {   // large batch, 16-byte aligned rows of 1-4 KB: persistent bulk-copy ring
+    constexpr int NV = 32 / VEC;           // 32 elements per lane and operand: C <= 1024
+    if (p.B >= 1024 && p.C * (int64_t)sizeof(T) >= 1024 && p.C <= 32 * VEC * NV && ring_enabled()) {
+      if (launch_ring<T, VEC, NV>(p, stream) == 0) return check_launch("dkd_logit_kd_fwdbwd: ring");
+    }
+  }
   if (p.B >= 1024 && nchunk64 <= 4) {   // large batch: fold in a second launch
     launch_mode<T, VEC, 64, false>(p, nchunk64, grid, stream);   // 2-warp CTAs (4-warp measured 3 % slower)
     int rc = check_launch("dkd_logit_kd_fwdbwd");

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as Fn
-from .features import forward_with_features, unwrap
+from .features import forward_with_features, needed_layers, unwrap
 from .misc import len_keep_of, saliency_scores
 
 _FEATURE_TYPES = ("vitkd", "lrkd", "diffkd", "curkd", "saliency_mgd", "wasskd", "mgd")
@@ -88,8 +88,9 @@ class DistillationLoss(nn.Module):
         with torch.no_grad():
             if kind in ('soft', 'hard'):
                 teacher_logits = self.teacher_model(inputs)
-            else:
-                teacher_logits, teacher_features = forward_with_features(self.teacher_model, inputs)
+            else:   # hooks only on the blocks this type reads; the list keeps its 12 slots
+                teacher_logits, teacher_features = forward_with_features(self.teacher_model, inputs,
+                                                                         layers=needed_layers(kind, args))
 
         if kind in ('soft', 'hard'):
             smoothing = _fusable_base(self.base_criterion)

@@ -63,7 +63,8 @@ def _oracle(kind, z, zk, zt, y, alpha, tau, smoothing=0.1):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,C,int_labels", [(1, 1000, False), (7, 100, False), (5, 1001, True), (3, 21843, False),
                                             (256, 1000, False), (33, 4100, True), (2, 8, False),
-                                            (1500, 1000, False), (1100, 2000, True), (1025, 104, False)])   # >= 1024: streaming kernel
+                                            (1500, 1000, False), (1100, 2000, True), (1025, 104, False),
+                                            (2048, 512, False), (1337, 1000, True)])   # B >= 1024 and 1-4 KB rows: bulk-copy ring kernel
 def test_logit_shapes_and_dtypes(kind, dtype, B, C, int_labels):
     from deltakd_b200 import functional as Fn
     from deltakd_b200 import synth
@@ -140,3 +141,24 @@ def test_invalid_type_raises():
     crit = DistillationLoss(call_base_loss(c.args), c.teacher, "aaakd", 0.1, 3.0)
     with pytest.raises(ValueError):
         crit(torch.zeros(8, 3, 2, 2, device="cuda"), c.outputs, c.student, None, c.labels, c.args)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("int_labels", [False, True])
+def test_base_ce_alone_large_batch(dtype, int_labels):
+    """distillation_type 'none' at a ring-kernel size: base CE only (kd_kind 0), both label kinds, ragged last warp."""
+    from deltakd_b200 import functional as Fn
+    from deltakd_b200 import synth
+    B, C = 2051, 1000
+    z, _, _, y = synth.make_logits(B, C, seed=5, int_labels=int_labels)
+    zc = z.to(dtype).cuda().requires_grad_(True)
+    yc = y.cuda() if int_labels else y.to(dtype).cuda()
+    loss = Fn.logit_kd_loss(zc, None, None, yc, kd_kind="none", smoothing=0.1)
+    loss.backward()
+    zo = zc.detach().double().cpu().requires_grad_(True)
+    yo = y if int_labels else yc.double().cpu()
+    ref = O.base_loss(zo, yo, "label_smoothing" if int_labels else "soft_target", 0.1)
+    ref.backward()
+    lt, gt = (LOSS_RTOL, GRAD_RTOL) if dtype == torch.float32 else (BF16_LOSS_RTOL, BF16_GRAD_RTOL)
+    assert abs(loss.item() - ref.item()) <= lt * abs(ref.item())
+    assert rel_err(zc.grad.float(), zo.grad) < gt
