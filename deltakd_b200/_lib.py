@@ -32,7 +32,11 @@ SIGNATURES = {
     "dkd_check_device": (_i, []),
     "dkd_launch_count": (C.c_ulonglong, []),
     "dkd_logit_kd_workspace_bytes": (_sz, [_i64]),
-    "dkd_logit_kd_fwdbwd": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _i, _f, _f, _f, _p, _p, _p, _p, _sz, _p]),
+    "dkd_logit_kd_fwdbwd": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _i, _f, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "dkd_step_workspace_bytes": (_sz, []),
+    "dkd_step_epilogue": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _f, _f, _f, _f, _f, _f, _i, _f, _f, _i, _i, _p, _p, _sz, _p]),
+    "dkd_topk_hits": (_i, [_p, _p, _i64, _i64, _i, _i, _i, _p, _p]),
+    "dkd_mix_batch": (_i, [_p, _i64, _i64, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "dkd_mask_rank": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "dkd_scale_if_not_one": (_i, [_p, _i64, _p, _i64, _i, _p, _p]),
     "dkd_align_mse_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),

@@ -53,6 +53,7 @@ struct LogitKdParams {
   int64_t B, C;
   int label_kind, kd_kind;
   float smoothing, alpha, tau;
+  const float* mix_lam;   // int labels only: if set, row r's target is lam * smooth_onehot(y[r]) + (1 - lam) * smooth_onehot(y[B-1-r])
 };
 
 // NV > 0: row cached in registers (C <= kThreads*VEC*NV).  NV == 0: streaming (re-read) path.
@@ -75,6 +76,11 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   const int kd_kind = KK == kRuntimeMode ? p.kd_kind : KK;
   const int tid = THREADS == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x;   // THREADS == 32: one warp per row
   const int64_t label = label_kind == 1 ? reinterpret_cast<const int64_t*>(p.y)[row] : -1;
+  // Mixup / CutMix targets generated on the fly (timm mixup_target, tools/train.py:288-295 + engine.py:16-18): the
+  // [B, C] soft-label tensor is never materialised — 5 instead of 6 row streams.  label2 = -1 when not mixing.
+  const bool mixing = label_kind == 1 && p.mix_lam != nullptr;
+  const int64_t label2 = mixing ? reinterpret_cast<const int64_t*>(p.y)[p.B - 1 - row] : -1;
+  const float lam = mixing ? __ldg(p.mix_lam) : 1.f;
   const float invT = kd_kind == 1 ? 1.f / p.tau : 1.f;
 
   constexpr int NVR = NV > 0 ? NV : 1;
@@ -204,6 +210,8 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
             T2[1] = add2(T2[1], A);
             if (col + v == label) t[2] = a[v];
             if (col + v + 1 == label) t[2] = a[v + 1];
+            if (col + v == label2) t[0] = a[v];
+            if (col + v + 1 == label2) t[0] = a[v + 1];
           }
           a[v] = ea.x; a[v + 1] = ea.y;
           if (kd_kind == 1) {
@@ -230,7 +238,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
         const float ea = fexp2(a[v], kL2e, mx[0] * kL2e);
         s[0] += ea;
         if (label_kind == 0) { t[0] += d[v]; t[1] += d[v] * a[v]; }
-        else { t[1] += a[v]; if (col + v == label) t[2] = a[v]; }
+        else { t[1] += a[v]; if (col + v == label) t[2] = a[v]; if (col + v == label2) t[0] = a[v]; }
         if (NV > 0) a[v] = ea;
         if (kd_kind == 1) {
           const float eb = fexp2(c[v], invT * kL2e, mx[2] * kL2e), es = fexp2(b[v], invT * kL2e, mx[1] * kL2e);
@@ -259,7 +267,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   if constexpr (PACKED) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) s[k] = S2[k].x + S2[k].y;
-    t[0] = T2[0].x + T2[0].y;
+    if (label_kind == 0) t[0] = T2[0].x + T2[0].y;   // (int labels: t[0] carries z[label2] of the mixed target)
     t[1] = T2[1].x + T2[1].y;
   }
   block_sum<8, THREADS>(st8, scratch);
@@ -272,7 +280,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   float base_row, kd_row = 0.f;
   if (label_kind < 0) base_row = 0.f;
   else if (label_kind == 0) base_row = lse0 * t[0] - t[1];
-  else base_row = (1.f - p.smoothing) * (lse0 - t[2]) + p.smoothing * (lse0 - t[1] / Cf);
+  else base_row = (1.f - p.smoothing) * (lse0 - (lam * t[2] + (1.f - lam) * t[0])) + p.smoothing * (lse0 - t[1] / Cf);
   float lse1 = 0.f, lse2 = 0.f;
   if (kd_kind == 1) {
     lse1 = mx[1] + __logf(s[1]);
@@ -292,7 +300,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
   //   g1 = es * k1 - et * k2 (soft KD)     | es * k1 - onehot * wk                      (hard KD)
   const float k0 = (label_kind == 0 ? inv_s0 * t[0] : inv_s0) * wb;
   const float k1 = inv_s1 * wk, k2 = inv_s2 * wk;
-  const float sm_wb = p.smoothing / Cf * wb, hot_wb = (1.f - p.smoothing) * wb;
+  const float sm_wb = p.smoothing / Cf * wb, hot_wb = (1.f - p.smoothing) * wb * lam, hot2_wb = (1.f - p.smoothing) * wb * (1.f - lam);
   T* gz = label_kind >= 0 ? gz_row : nullptr;
   T* gzk = kd_kind ? gzk_row : nullptr;
   auto pass3 = [&](int it, float (&a)[VEC], float (&b)[VEC], float (&c)[VEC], float (&d)[VEC]) {
@@ -310,6 +318,8 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
             r0 = fma2(e0, K0, NSM);
             if (col + v == label) r0.x -= hot_wb;
             if (col + v + 1 == label) r0.y -= hot_wb;
+            if (col + v == label2) r0.x -= hot2_wb;
+            if (col + v + 1 == label2) r0.y -= hot2_wb;
           }
           g0[v] = r0.x; g0[v + 1] = r0.y;
           if (kd_kind == 1) {
@@ -327,7 +337,7 @@ __device__ __forceinline__ void logit_row(const LogitKdParams& p, int64_t row, c
       for (int v = 0; v < VEC; ++v) {
         const float e0 = NV > 0 ? a[v] : fexp(a[v] - mx[0]);
         if (label_kind == 0) g0[v] = fmaf(e0, k0, -(d[v] * wb));
-        else g0[v] = fmaf(e0, k0, -sm_wb) - (col + v == label ? hot_wb : 0.f);
+        else g0[v] = fmaf(e0, k0, -sm_wb) - (col + v == label ? hot_wb : 0.f) - (col + v == label2 ? hot2_wb : 0.f);
         if (kd_kind == 1) {
           const float es = NV > 0 ? b[v] : fexp(b[v] * invT - mx[1]);
           const float et = NV > 0 ? c[v] : fexp(c[v] * invT - mx[2]);
@@ -704,7 +714,7 @@ size_t dkd_logit_kd_workspace_bytes(int64_t B) {
 
 int dkd_logit_kd_fwdbwd(const void* outputs, const void* outputs_kd, const void* teacher_logits,
                         const void* labels, int label_kind, int kd_kind, int64_t B, int64_t C, int dtype,
-                        float smoothing, float alpha, float tau, void* g_outputs, void* g_outputs_kd,
+                        float smoothing, float alpha, float tau, const float* mix_lam, void* g_outputs, void* g_outputs_kd,
                         float* loss_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream) {
   using namespace dkd;
   int rc = dkd_check_device();
@@ -727,6 +737,8 @@ int dkd_logit_kd_fwdbwd(const void* outputs, const void* outputs_kd, const void*
   p.row_kd = p.row_base + B;
   p.B = B; p.C = C; p.label_kind = label_kind; p.kd_kind = kd_kind;
   p.smoothing = smoothing; p.alpha = alpha; p.tau = tau;
+  DKD_REQUIRE(mix_lam == nullptr || label_kind == 1, DKD_E_UNSUPPORTED, "dkd_logit_kd_fwdbwd: mix_lam needs int64 labels (label_kind 1)");
+  p.mix_lam = mix_lam;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return dtype == DKD_F32 ? dispatch_vec<float>(p, st) : dispatch_vec<__nv_bfloat16>(p, st);
 }

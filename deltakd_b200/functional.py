@@ -137,7 +137,7 @@ def _logit_ws_bytes(B: int) -> int:
 
 class _LogitKD(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, outputs, outputs_kd, teacher_logits, labels, label_kind, kd_kind, smoothing, alpha, tau, parts_out):
+    def forward(ctx, outputs, outputs_kd, teacher_logits, labels, label_kind, kd_kind, smoothing, alpha, tau, parts_out, mix_lam=None):
         ref = outputs if outputs is not None else outputs_kd
         B, Cn = ref.shape
         dt = _dtype_code(ref)
@@ -148,7 +148,7 @@ class _LogitKD(torch.autograd.Function):
         loss3 = torch.empty(3, dtype=torch.float32, device=ref.device)
         ws = _workspace(ref.device, "logit_kd", _logit_ws_bytes(B))
         rc = _LOGIT_FN(_ptr(outputs), _ptr(outputs_kd), _ptr(teacher_logits), _ptr(labels),
-                       label_kind, kd_kind, B, Cn, dt, float(smoothing), float(alpha), float(tau),
+                       label_kind, kd_kind, B, Cn, dt, float(smoothing), float(alpha), float(tau), _ptr(mix_lam),
                        _ptr(g0), _ptr(g1), loss3.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
         if rc:
             _lib.check(rc, "dkd_logit_kd_fwdbwd")
@@ -160,15 +160,17 @@ class _LogitKD(torch.autograd.Function):
     @_once
     def backward(ctx, grad_total):
         g0, g1 = _take_grads(ctx)
-        return _rescale_(grad_total, g0, g1) + (None,) * 8
+        return _rescale_(grad_total, g0, g1) + (None,) * 9
 
 
 def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, smoothing: float = 0.1,
-                  alpha: float = 0.0, tau: float = 1.0, return_parts: bool = False):
+                  alpha: float = 0.0, tau: float = 1.0, return_parts: bool = False, mix_lam=None):
     """Fused base CE (+ soft / hard KD) on logits.
 
     labels: float [B,C] soft targets -> SoftTargetCrossEntropy; int64 [B] -> LabelSmoothingCrossEntropy(smoothing);
     None -> KD term only (returns alpha*kd).  kd_kind in {"none","soft","hard"}.
+    mix_lam (fp32 device scalar, int labels only): the target of row r is timm Mixup's soft label
+    lam*smooth_onehot(labels[r]) + (1-lam)*smooth_onehot(labels[B-1-r]), generated inside the kernel.
     Returns the 0-dim fp32 total `base*(1-alpha) + kd*alpha` (or base alone for "none").
     """
     kk = {"none": 0, "soft": 1, "hard": 2}[kd_kind]
@@ -209,8 +211,12 @@ def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, 
         outputs = _contig(outputs)
     if labels is not None:
         labels = _contig(_plain(labels))
+    if mix_lam is not None:
+        if lk != 1:
+            raise ValueError("mix_lam needs int64 class labels")
+        mix_lam = mix_lam.detach().to(device=ref.device, dtype=torch.float32).reshape(1)
     parts = []
-    total = _LogitKD.apply(outputs, outputs_kd, teacher_logits, labels, lk, kk, smoothing, alpha, tau, parts)
+    total = _LogitKD.apply(outputs, outputs_kd, teacher_logits, labels, lk, kk, smoothing, alpha, tau, parts, mix_lam)
     return (total, parts[0]) if return_parts else total
 
 

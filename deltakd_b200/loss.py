@@ -24,11 +24,22 @@ from .misc import len_keep_of, saliency_scores
 _FEATURE_TYPES = ("vitkd", "lrkd", "diffkd", "curkd", "saliency_mgd", "wasskd", "mgd")
 
 
-class SoftTargetCrossEntropy(nn.Module):
-    """mean_b sum_c -y log_softmax(x) (timm 0.9.12 class of the same name; loss.py:2,247)."""
+def _labels_args(labels, smoothing):
+    """(labels tensor, smoothing, mix_lam) for the fused logit kernel: `MixedLabels` (deltakd_b200.mixup) carry int64 ids +
+    lam and the kernel builds timm's mixed soft label itself."""
+    from .mixup import MixedLabels
+    if isinstance(labels, MixedLabels):
+        return labels.target, labels.smoothing, labels.lam
+    return labels, smoothing, None
 
-    def forward(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        return Fn.logit_kd_loss(x, None, None, target, kd_kind="none")
+
+class SoftTargetCrossEntropy(nn.Module):
+    """mean_b sum_c -y log_softmax(x) (timm 0.9.12 class of the same name; loss.py:2,247).  `target` is the dense
+    [B, C] soft label, or the `MixedLabels` our Mixup returns (the soft label is then generated inside the kernel)."""
+
+    def forward(self, x: torch.Tensor, target) -> torch.Tensor:
+        target, smoothing, lam = _labels_args(target, 0.0)
+        return Fn.logit_kd_loss(x, None, None, target, kd_kind="none", smoothing=smoothing, mix_lam=lam)
 
 
 class LabelSmoothingCrossEntropy(nn.Module):
@@ -95,8 +106,9 @@ class DistillationLoss(nn.Module):
         if kind in ('soft', 'hard'):
             smoothing = _fusable_base(self.base_criterion)
             if smoothing is not None:  # one launch: base CE + KD + both gradients + mix (loss.py:35,57-67,241)
+                labels, smoothing, lam = _labels_args(labels, smoothing)
                 return Fn.logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, kd_kind=kind,
-                                        smoothing=smoothing, alpha=self.alpha, tau=self.tau)
+                                        smoothing=smoothing, alpha=self.alpha, tau=self.tau, mix_lam=lam)
             base_loss = self.base_criterion(outputs, labels)
             kd = Fn.logit_kd_loss(None, outputs_kd, teacher_logits, None, kd_kind=kind,
                                   alpha=self.alpha, tau=self.tau)  # = alpha * kd

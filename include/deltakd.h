@@ -72,6 +72,11 @@ DKD_API unsigned long long dkd_launch_count(void);
  *                                         (outputs_kd / teacher_logits may be NULL when kd_kind==0)
  *   labels      : label_kind 0 -> soft targets [B, C] `dtype`; 1 -> int64 class ids [B];
  *                 -1 -> no base term (outputs/labels/g_outputs ignored; total = alpha * kd)
+ *   mix_lam     : NULL, or (label_kind 1 only) a DEVICE fp32 scalar lam: the target of row r is then the Mixup / CutMix
+ *                 soft label timm's Mixup would have built (tools/train.py:288-295, engine.py:16-18: mixup_target)
+ *                     lam * smooth_onehot(labels[r]) + (1 - lam) * smooth_onehot(labels[B-1-r]),
+ *                 smooth_onehot(k)[c] = smoothing/C + (1 - smoothing) * [c == k], generated inside the kernel: the
+ *                 [B, C] soft-label tensor is neither written by the mixer nor read by the loss
  *   kd_kind     : 0 none (loss = base), 1 soft (temperature `tau`), 2 hard (teacher argmax, first max)
  *   g_outputs, g_outputs_kd : [B, C] `dtype` gradients of the returned loss (NULL -> not written)
  *   loss_out    : fp32[3] = { total, base, kd }
@@ -81,8 +86,9 @@ DKD_API unsigned long long dkd_launch_count(void);
 DKD_API size_t dkd_logit_kd_workspace_bytes(int64_t B);
 DKD_API int dkd_logit_kd_fwdbwd(const void* outputs, const void* outputs_kd, const void* teacher_logits,
                         const void* labels, int label_kind, int kd_kind, int64_t B, int64_t C, int dtype,
-                        float smoothing, float alpha, float tau, void* g_outputs, void* g_outputs_kd,
-                        float* loss_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+                        float smoothing, float alpha, float tau, const float* mix_lam, void* g_outputs,
+                        void* g_outputs_kd, float* loss_out, void* workspace, size_t workspace_bytes,
+                        dkd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Mask selection by rank (bit-exact integer work).  Replaces the double argsort of
@@ -277,6 +283,38 @@ DKD_API int dkd_head_copy(const void* src, void* dst, int64_t B, int H, int N, i
 DKD_API size_t dkd_colsum_workspace_bytes(int64_t M, int N);
 DKD_API int dkd_colsum(const void* a, int64_t M, int N, int dtype, float* out, void* workspace, size_t workspace_bytes,
                        dkd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step epilogue and input-side helpers (rank 4): what tools/engine.py does around the criterion.
+ *
+ * dkd_step_epilogue — timm NativeScaler (torch GradScaler: unscale, inf/nan check, skipped step, scale update) +
+ * gradient-norm clipping (`--clip-grad`: torch clip_grad_norm_) + AdamW (torch.optim.AdamW as built by timm
+ * create_optimizer('adamw')) + timm ModelEma update, engine.py:58-69, in two launches over FLAT fp32 buffers of `n`
+ * elements (parameters, gradients of the SCALED loss, exp_avg, exp_avg_sq, and the EMA copy or NULL).  Elements
+ * [0, n_decay) receive decoupled weight decay, the rest (biases, norm scales: timm's no-decay group) do not.
+ *   lr    : DEVICE fp32 scalar (a scheduler or a captured graph updates it in place)
+ *   state : DEVICE fp32[8], owned by the caller, initialised to {loss_scale, 0, 0, 0, 0, 0, 0, 0}:
+ *           [0] loss scale  [1] growth tracker  [2] optimizer step count  [3] 1 if the last step was skipped (non-finite
+ *           gradients)  [4] total norm of the unscaled gradients  [5] clip coefficient applied.  Never read back by the host.
+ *   clip_grad <= 0 disables clipping; dynamic_scale 0 keeps the loss scale fixed (use loss scale 1 for bf16 / fp32).
+ *   zero_grad 1 clears the gradient buffer in the same pass (optimizer.zero_grad(), engine.py:58).
+ *   workspace : >= dkd_step_workspace_bytes() bytes, zero-initialised once by the caller.
+ */
+DKD_API size_t dkd_step_workspace_bytes(void);
+DKD_API int dkd_step_epilogue(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
+                              int64_t n_decay, const float* lr, float beta1, float beta2, float eps, float weight_decay,
+                              float clip_grad, float ema_decay, int dynamic_scale, float growth_factor,
+                              float backoff_factor, int growth_interval, int zero_grad, float* state, void* workspace,
+                              size_t workspace_bytes, dkd_stream_t stream);
+/* hits[0] = #rows whose target logit ranks < k0, hits[1] = ... < k1 (timm.utils.accuracy(output, target, topk=(k0, k1)),
+ * engine.py:53-56: acc_k = 100 * hits / B); ties rank lower index first.  target int64 [B], hits fp32[2] (overwritten). */
+DKD_API int dkd_topk_hits(const void* logits, const int64_t* target, int64_t B, int64_t C, int dtype, int k0, int k1,
+                          float* hits, dkd_stream_t stream);
+/* timm.data.Mixup (mode 'batch') image mixing, in place on x fp32 [B, CH, H, W] (train.py:288-295, engine.py:16-18):
+ * use_cutmix 0: x[b] = lam * x[b] + (1 - lam) * x[B-1-b];  1: the box [y0,y1) x [x0,x1) of x[b] and x[B-1-b] is swapped.
+ * lam is a DEVICE fp32 scalar (the same one dkd_logit_kd_fwdbwd takes as mix_lam). */
+DKD_API int dkd_mix_batch(float* x, int64_t B, int64_t CH, int H, int W, const float* lam, int use_cutmix, int y0, int y1,
+                          int x0, int x1, dkd_stream_t stream);
 
 #ifdef __cplusplus
 }
