@@ -34,7 +34,8 @@ SIGNATURES = {
     "dkd_logit_kd_workspace_bytes": (_sz, [_i64]),
     "dkd_logit_kd_fwdbwd": (_i, [_p, _p, _p, _p, _i, _i, _i64, _i64, _i, _f, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
     "dkd_step_workspace_bytes": (_sz, []),
-    "dkd_step_epilogue": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, _f, _f, _f, _f, _f, _f, _i, _f, _f, _i, _i, _p, _p, _sz, _p]),
+    "dkd_step_epilogue": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _p, C.c_double, C.c_double, _f, _f, _f, C.c_double, _i, _f, _f, _i, _i, _p, _p,
+                               _sz, _p]),
     "dkd_topk_hits": (_i, [_p, _p, _i64, _i64, _i, _i, _i, _p, _p]),
     "dkd_mix_batch": (_i, [_p, _i64, _i64, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "dkd_mask_rank": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),

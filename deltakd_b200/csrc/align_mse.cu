@@ -11,12 +11,21 @@
 //   4. gemm_tn + StoreRows epilogue   : g_s[:,off:,:] = G W    (rows scattered into [B,Ts,Ds], CLS rows zeroed)
 //   5. gemm_nt (split-K, MN-major)    : g_W += G^T S, g_b += G^T 1 (ones-column trick)
 //   6. fold_partials                  : loss += sum of the per-CTA partials, fixed order (deterministic)
+#include <stdlib.h>
+
+#include "align_fused.cuh"
 #include "align_ops.cuh"
 
 namespace dkd {
 namespace {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// DKD_ALIGN_FUSED = 0 keeps the three-launch form (forward, dgrad, wgrad) for A/B runs
+bool align_fused_enabled() {
+  static const bool on = [] { const char* e = getenv("DKD_ALIGN_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 struct Workspace {
   __nv_bfloat16 *S, *Wp, *Wt, *G, *ones;
@@ -73,6 +82,25 @@ int dkd_align_mse_fwdbwd(const void* s, const void* t, const float* W, const flo
   if (rc != DKD_OK) return rc;
   rc = launch_weight_to_planes(W, Dt, Ds, P, ws.Wp, want_grads ? ws.Wt : nullptr, st);
   if (rc != DKD_OK) return rc;
+
+  // 3-4 fused: forward + residual + dgrad in one persistent kernel (align_fused.cuh); the G planes it leaves feed step 5
+  if (align_fused_enabled()) {
+    int grid = 0;
+    const char* what = "dkd_align_mse_fwdbwd: fused forward + dgrad";
+    rc = P == 2 ? align_fused_fwd_dgrad_t<2>(ws.S, ws.Wp, bias, t, dtype == DKD_BF16, Tt, t_off, n_tok, ws.G, ws.partials, 2.f * scale,
+                                             g_s, Ts, s_off, dtype == DKD_BF16, 1.f, M, st, &grid, what)
+                : align_fused_fwd_dgrad_t<1>(ws.S, ws.Wp, bias, t, dtype == DKD_BF16, Tt, t_off, n_tok, ws.G, ws.partials, 2.f * scale,
+                                             g_s, Ts, s_off, dtype == DKD_BF16, 1.f, M, st, &grid, what);
+    if (rc != DKD_OK) return rc;
+    rc = launch_fold_partials(ws.partials, grid, scale, loss, st);
+    if (rc != DKD_OK) return rc;
+    if (g_W || g_b) {
+      DKD_REQUIRE(g_W != nullptr, DKD_E_UNSUPPORTED, "dkd_align_mse_fwdbwd: g_b without g_W is not supported");
+      rc = align_wgrad(ws.G, ws.S, ws.ones, g_W, g_b, M, Ds, Dt, P, 1.f, st, "dkd_align_mse_fwdbwd: wgrad GEMM");
+      if (rc != DKD_OK) return rc;
+    }
+    return DKD_OK;
+  }
 
   // 3. forward GEMM + residual epilogue
   int grid = 0;

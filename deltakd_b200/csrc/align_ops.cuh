@@ -5,6 +5,7 @@
 //   align_dgrad        : g_s[:, off:, :] = alpha * G W                (gemm_tn, rows scattered, special tokens zeroed)
 //   align_wgrad        : g_W = alpha * G^T S, g_b = alpha * G^T 1     (gemm_nt split-K, ones-column trick)
 #pragma once
+#include <stdlib.h>
 #include "epilogues.cuh"
 #include "gemm_nt.cuh"
 #include "planes.cuh"
@@ -15,6 +16,9 @@ using AlignCfg1 = GemmCfg<192, 1, 4, 2, 128, 1, 8>;   // one plane per stage (bf
 using AlignCfg2 = GemmCfg<192, 1, 2, 2, 128, 2, 8>;   // both planes per stage (bf16x3), 2 stages of 80 KB, 8 epilogue warps
 using AlignWgradCfg1 = GemmNtCfg<3, true, 208, 0, 4>;
 using AlignWgradCfg2 = GemmNtCfg<3, true, 208, 0, 2, 64, false, 2>;   // both planes per stage: 2 stages of 96 KB
+// ... as 3-CTA clusters (the three 128-wide teacher-channel tiles of one row split) with the S block multicast
+using AlignWgradCfg1C = GemmNtCfg<3, true, 208, 0, 4, 64, false, 1, 3>;
+using AlignWgradCfg2C = GemmNtCfg<3, true, 208, 0, 2, 64, false, 2, 3>;
 
 template <class Cfg>
 inline int align_forward_rows_t(const __nv_bfloat16* S, const __nv_bfloat16* Wp, const float* bias, float* A, int64_t M, int Ds, int Dt,
@@ -121,17 +125,33 @@ inline int align_wgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bf
   p.ep.D = g_W; p.ep.Dcol = g_b; p.ep.ldd = Ds; p.ep.alpha = alpha;
   p.ld.ldd = Ds; p.ld.na_tiles = Dt / 128; p.ld.b_col0 = 0;
   p.ld.total_row_blocks = (int)((M + Cfg::KROWS - 1) / Cfg::KROWS);
-  nt_make_splits(p.ld.total_row_blocks, kNumSMs / p.ld.na_tiles, &p.ld.splits, &p.ld.row_blocks_per_split);
   p.nterms = P == 2 ? 3 : 1;
-  const int grid = min(kNumSMs, p.ld.na_tiles * p.ld.splits);
-  auto kern = gemm_nt_kernel<Cfg, L>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+  if constexpr (Cfg::CLUSTER > 1) {
+    static const int resident = [] {
+      auto kern = gemm_nt_kernel<Cfg, L>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+      return max_resident_clusters(kern, Cfg::CLUSTER, Cfg::THREADS, Cfg::SMEM);
+    }();
+    nt_make_splits(p.ld.total_row_blocks, resident, &p.ld.splits, &p.ld.row_blocks_per_split);
+    launch_gemm_nt<Cfg, L>(p, min(resident, p.ld.splits) * Cfg::CLUSTER, st);
+  } else {
+    nt_make_splits(p.ld.total_row_blocks, kNumSMs / p.ld.na_tiles, &p.ld.splits, &p.ld.row_blocks_per_split);
+    launch_gemm_nt<Cfg, L>(p, min(kNumSMs, p.ld.na_tiles * p.ld.splits), st);
+  }
   return check_launch(what);
+}
+
+// DKD_ALIGN_WGRAD_CLUSTER = 1 | 3
+inline int align_wgrad_cluster() {
+  static const int v = [] { const char* e = getenv("DKD_ALIGN_WGRAD_CLUSTER"); const int x = e ? atoi(e) : 3; return x == 1 ? 1 : 3; }();
+  return v;
 }
 
 inline int align_wgrad(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bfloat16* ones, float* g_W, float* g_b, int64_t M, int Ds, int Dt,
                        int P, float alpha, cudaStream_t st, const char* what) {
+  if (align_wgrad_cluster() == 3 && Dt == 384)
+    return P == 2 ? align_wgrad_t<AlignWgradCfg2C>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what)
+                  : align_wgrad_t<AlignWgradCfg1C>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what);
   return P == 2 ? align_wgrad_t<AlignWgradCfg2>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what)
                 : align_wgrad_t<AlignWgradCfg1>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what);
 }

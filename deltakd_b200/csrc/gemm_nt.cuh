@@ -23,7 +23,6 @@ template <int NB_BOXES_, bool ONES_, int N0_, int N1_, int STAGES_, int KROWS_ =
           int CLUSTER_ = 1>
 struct GemmNtCfg {
   static constexpr int CLUSTER = CLUSTER_;
-  static_assert(CLUSTER_ == 1 || PLANES_ == 1, "the cluster form streams one plane pair per stage");
   static constexpr int PLANES = PLANES_;
   static constexpr bool A_KMAJOR = A_KMAJOR_;       // A tile is [128 rows x 64 k] K-major (one box) instead of two MN-major boxes
   static constexpr int NA = 128;                      // UMMA M
@@ -117,8 +116,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           for (int rb = it.rb0; rb < it.rb1; ++rb) {
             mbar_wait(&empty[s], ph ^ 1);
             mbar_expect_tx(&full[s], Loader::TX_BYTES);
-            Loader::issue_planes(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
-            Loader::issue_planes(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES, &full[s]);
+            if constexpr (Cfg::CLUSTER > 1) {
+              Loader::issue_planes_cluster(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], crank);
+              Loader::issue_planes_cluster(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES,
+                                           &full[s], crank);
+            } else {
+              Loader::issue_planes(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
+              Loader::issue_planes(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES, &full[s]);
+            }
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
           }
         } else {
@@ -293,7 +298,7 @@ struct NtPlainLoader {
   using Params = NtPlainParams;
   using Item = NtItem;
   static constexpr uint32_t TX_BYTES = Cfg::STAGE_BYTES;
-  static __device__ __forceinline__ int num_items(const Params& p) { return p.na_tiles * p.splits; }
+  static __device__ __forceinline__ int num_items(const Params& p) { return Cfg::CLUSTER > 1 ? p.splits : p.na_tiles * p.splits; }
   static __device__ __forceinline__ void prefetch(const Params& p) {
     sm100::tma_prefetch_desc(&p.tmA);
     sm100::tma_prefetch_desc(&p.tmB);
@@ -321,6 +326,33 @@ struct NtPlainLoader {
       sm100::tma_load_3d(b + (size_t)i * Cfg::BOX_BYTES, &p.tmB, bar, it.b_col0 + i * 64, rb * Cfg::KROWS, pb);
     if constexpr (Cfg::ONES)  // plane 0 of the ones tile is {1,0,0,...}; its lo plane is all zero
       sm100::tma_load_3d(b + (size_t)Cfg::NB_BOXES * Cfg::BOX_BYTES, &p.tmOnes, bar, 0, 0, pb);
+  }
+  // ---- cluster form: the CLUSTER CTAs of a cluster are the A column tiles (na_tiles == CLUSTER) of ONE row split: they
+  // contract over the same rows of B, so CTA `crank` fetches B box `crank` and multicasts it (NB_BOXES == CLUSTER).
+  static __device__ __forceinline__ int num_items_cluster(const Params& p) { return p.splits; }
+  static __device__ __forceinline__ void decode_cluster(const Params& p, int item, int crank, Item& it) {
+    it.rb0 = item * p.row_blocks_per_split;
+    it.rb1 = min(it.rb0 + p.row_blocks_per_split, p.total_row_blocks);
+    it.a_col0 = crank * 128;
+    it.b_col0 = p.b_col0;
+    it.d_off = (int64_t)crank * 128 * p.ldd;
+    it.dcol_off = crank * 128;
+    it.aux = 0;
+  }
+  static __device__ __forceinline__ void issue_planes_cluster(const Params& p, const Item& it, int pa, int pb, int rb, uint8_t* a, uint8_t* b,
+                                                              uint64_t* bar, int crank) {
+    static_assert(Cfg::CLUSTER == 1 || Cfg::NB_BOXES == Cfg::CLUSTER, "one B box per CTA of the cluster");
+    sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
+    sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
+    sm100::tma_load_3d_mc(b + (size_t)crank * Cfg::BOX_BYTES, &p.tmB, bar, it.b_col0 + crank * 64, rb * Cfg::KROWS, pb,
+                          (uint16_t)((1u << Cfg::CLUSTER) - 1u));
+    if constexpr (Cfg::ONES) sm100::tma_load_3d(b + (size_t)Cfg::NB_BOXES * Cfg::BOX_BYTES, &p.tmOnes, bar, 0, 0, pb);
+  }
+  static __device__ __forceinline__ void issue_cluster(const Params& p, const Item& it, int term, int nterms, int rb, uint8_t* a, uint8_t* b,
+                                                       uint64_t* bar, int crank) {
+    int pa, pb;
+    term_planes(term, nterms, pa, pb);
+    issue_planes_cluster(p, it, pa, pb, rb, a, b, bar, crank);
   }
 };
 

@@ -25,6 +25,8 @@ struct StepParams {
   int64_t n, n_decay;            // elements; [0, n_decay) get weight decay, [n_decay, n) do not (biases, norms)
   const float* lr;               // device scalar (schedulers and captured graphs update it in place)
   float beta1, beta2, eps, weight_decay, clip_grad, ema_decay;
+  double b1d, b2d;
+  float omb1, omb2, omd;         // 1 - beta1, 1 - beta2, 1 - ema_decay rounded from DOUBLE differences (as Python computes them)
   float growth, backoff; int growth_interval; int dynamic_scale;
   int zero_grad;
   float* st;
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(kStepThreads) step_update_kernel(StepParams q)
       const float t_new = q.st[2] + 1.f;
       s_coef = coef;
       s_skip = inf ? 1 : 0;
-      s_b1c = 1.f - powf(q.beta1, t_new);
-      s_b2c = 1.f - powf(q.beta2, t_new);
+      s_b1c = (float)(1.0 - pow((double)q.b1d, (double)t_new));
+      s_b2c = (float)(1.0 - pow((double)q.b2d, (double)t_new));
     }
     __syncthreads();
   }
@@ -105,11 +107,11 @@ __global__ void __launch_bounds__(kStepThreads) step_update_kernel(StepParams q)
   auto upd = [&](float& p, float gs, float& m, float& v, float& e, bool decay) {
     const float g = gs * coef;
     if (decay) p *= 1.f - lr * q.weight_decay;            // decoupled weight decay (torch.optim.AdamW)
-    m = fmaf(q.beta1, m, (1.f - q.beta1) * g);
-    v = fmaf(q.beta2, v, (1.f - q.beta2) * g * g);
+    m = fmaf(q.beta1, m, q.omb1 * g);
+    v = fmaf(q.beta2, v, q.omb2 * g * g);
     const float denom = sqrtf(v) * inv_sqrt_b2c + q.eps;
     p -= step_size * (m / denom);
-    if (has_ema) e = fmaf(q.ema_decay, e, (1.f - q.ema_decay) * p);   // timm ModelEma: d * ema + (1 - d) * model
+    if (has_ema) e = fmaf(q.ema_decay, e, q.omd * p);   // timm ModelEma: d * ema + (1 - d) * model
   };
   if (!skip) {
     for (int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x; i < n4; i += stride) {
@@ -135,9 +137,8 @@ __global__ void __launch_bounds__(kStepThreads) step_update_kernel(StepParams q)
     for (int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x; i < n4; i += stride) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * kStepThreads + threadIdx.x; i < q.n; i += stride) q.g[i] = 0.f;
   }
-  // scaler / counters: the LAST CTA to arrive here would need a ticket; instead CTA 0 writes them — every CTA has
-  // already read st[0] and st[2] before it reaches its first store only if it read them above, so CTA 0 defers the
-  // write until the whole grid has passed the fold.  A second flag word counts the CTAs that finished reading.
+  // scaler state / counters: written by the LAST CTA to finish (arrival counter in flag[1]) — by then every CTA has read
+  // st[0], st[2] and the non-finite flag, so updating them cannot change another CTA's decision.
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -223,7 +224,7 @@ extern "C" {
 size_t dkd_step_workspace_bytes(void) { return (size_t)dkd::kStepMaxCtas * sizeof(double) + 256; }
 
 int dkd_step_epilogue(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n, int64_t n_decay,
-                      const float* lr, float beta1, float beta2, float eps, float weight_decay, float clip_grad, float ema_decay,
+                      const float* lr, double beta1, double beta2, float eps, float weight_decay, float clip_grad, double ema_decay,
                       int dynamic_scale, float growth_factor, float backoff_factor, int growth_interval, int zero_grad, float* state,
                       void* workspace, size_t workspace_bytes, dkd_stream_t stream) {
   using namespace dkd;
@@ -235,10 +236,12 @@ int dkd_step_epilogue(float* params, float* grads, float* exp_avg, float* exp_av
   DKD_REQUIRE(workspace_bytes >= dkd_step_workspace_bytes(), DKD_E_WORKSPACE, "%s: workspace too small", fn);
   DKD_REQUIRE(((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq) | ((uintptr_t)ema) | ((uintptr_t)workspace)) & 15) == 0,
               DKD_E_ALIGN, "%s: buffers must be 16-byte aligned", fn);
-  DKD_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps > 0.f, DKD_E_SHAPE, "%s: bad hyper-parameters", fn);
+  DKD_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps > 0.f && ema_decay >= 0.0 && ema_decay <= 1.0, DKD_E_SHAPE,
+              "%s: bad hyper-parameters", fn);
   StepParams q;
   q.p = params; q.g = grads; q.m = exp_avg; q.v = exp_avg_sq; q.ema = ema; q.n = n; q.n_decay = n_decay; q.lr = lr;
-  q.beta1 = beta1; q.beta2 = beta2; q.eps = eps; q.weight_decay = weight_decay; q.clip_grad = clip_grad; q.ema_decay = ema_decay;
+  q.beta1 = (float)beta1; q.beta2 = (float)beta2; q.eps = eps; q.weight_decay = weight_decay; q.clip_grad = clip_grad; q.ema_decay = (float)ema_decay;
+  q.b1d = beta1; q.b2d = beta2; q.omb1 = (float)(1.0 - beta1); q.omb2 = (float)(1.0 - beta2); q.omd = (float)(1.0 - ema_decay);
   q.growth = growth_factor; q.backoff = backoff_factor; q.growth_interval = growth_interval; q.dynamic_scale = dynamic_scale;
   q.zero_grad = zero_grad; q.st = state;
   q.flag = reinterpret_cast<unsigned int*>(workspace);                       // [0] non-finite, [1] arrival counter (zero on entry, reset on exit)

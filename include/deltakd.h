@@ -296,14 +296,15 @@ DKD_API int dkd_colsum(const void* a, int64_t M, int N, int dtype, float* out, v
  *   state : DEVICE fp32[8], owned by the caller, initialised to {loss_scale, 0, 0, 0, 0, 0, 0, 0}:
  *           [0] loss scale  [1] growth tracker  [2] optimizer step count  [3] 1 if the last step was skipped (non-finite
  *           gradients)  [4] total norm of the unscaled gradients  [5] clip coefficient applied.  Never read back by the host.
+ *   beta1, beta2, ema_decay are doubles: 1 - x is formed in double (as the Python reference does) before rounding to fp32.
  *   clip_grad <= 0 disables clipping; dynamic_scale 0 keeps the loss scale fixed (use loss scale 1 for bf16 / fp32).
  *   zero_grad 1 clears the gradient buffer in the same pass (optimizer.zero_grad(), engine.py:58).
  *   workspace : >= dkd_step_workspace_bytes() bytes, zero-initialised once by the caller.
  */
 DKD_API size_t dkd_step_workspace_bytes(void);
 DKD_API int dkd_step_epilogue(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
-                              int64_t n_decay, const float* lr, float beta1, float beta2, float eps, float weight_decay,
-                              float clip_grad, float ema_decay, int dynamic_scale, float growth_factor,
+                              int64_t n_decay, const float* lr, double beta1, double beta2, float eps, float weight_decay,
+                              float clip_grad, double ema_decay, int dynamic_scale, float growth_factor,
                               float backoff_factor, int growth_interval, int zero_grad, float* state, void* workspace,
                               size_t workspace_bytes, dkd_stream_t stream);
 /* hits[0] = #rows whose target logit ranks < k0, hits[1] = ... < k1 (timm.utils.accuracy(output, target, topk=(k0, k1)),

@@ -93,7 +93,20 @@ def test_topk_accuracy(dtype):
     z[torch.arange(0, 257, 3), t[::3]] += 4.0        # a good share of hits
     a1, a5 = accuracy(z.cuda(), t.cuda(), topk=(1, 5))
     r1, r5 = S.accuracy(z.float(), t, topk=(1, 5))
-    assert abs(a1.item() - r1.item()) < 1e-4 and abs(a5.item() - r5.item()) < 1e-4
+    # bf16 logits tie often and torch.topk's order among equal values is unspecified: the kernel ranks ties lower index
+    # first; it must sit between the strict (ties lose) and the lenient (ties win) counts, and equal torch when no target ties
+    zf = z.float()
+    zt = zf.gather(1, t.view(-1, 1))
+    hi_rank = (zf >= zt).sum(1) - 1          # ties all ahead of the target
+    lo_rank = (zf > zt).sum(1)               # ties all behind
+    for a, r, k in ((a1, r1, 1), (a5, r5, 5)):
+        lo = (hi_rank < k).float().mean().item() * 100
+        hi = (lo_rank < k).float().mean().item() * 100
+        assert lo - 1e-4 <= a.item() <= hi + 1e-4, (k, lo, a.item(), hi)
+        if lo == hi:
+            assert abs(a.item() - r.item()) < 1e-4
+    exact = ((zf > zt).sum(1) + ((zf == zt) & (torch.arange(1000).view(1, -1) < t.view(-1, 1))).sum(1))
+    assert abs(a5.item() - (exact < 5).float().mean().item() * 100) < 1e-4
     # tuple outputs of the distilled student are reduced by the caller (engine.py:50-51); small C clamps k
     a1, a5 = accuracy(z[:, :3].contiguous().cuda(), (t % 3).cuda(), topk=(1, 5))
     assert a5.item() == 100.0
