@@ -2,27 +2,31 @@
 // 277-289) for one Linear(192 -> 384) head:
 //     Y = S W^T + b ;  d = Y - t ;  loss += sum d^2 ;  G = gscale * d (bf16 planes, kept for the weight-gradient GEMM) ;
 //     g_s = G W
-// in ONE persistent tcgen05 kernel per layer.  Per 128-row tile the S planes stay in shared memory, W streams through a
-// ring in 64-row chunks of the teacher width (Dt), and the SAME shared-memory chunk is used twice: K-major as the B
-// operand of the forward MMA (Y_c = S W_c^T, K = Ds) and MN-major as the B operand of the dgrad MMA
-// (g_s += d_c W_c, K = the chunk's 64 teacher channels).  The residual chunk d_c goes TMEM -> registers (teacher
-// subtracted, loss accumulated) -> a 128-byte-swizzled K-major shared-memory tile -> A operand of dgrad (and source of the G store):
-// the G planes are never re-read from HBM for dgrad and the g_s accumulator (128 x 192 fp32) lives in TMEM across the
-// six chunks.  Compared with the three-launch form (forward, dgrad, wgrad) this removes the dgrad kernel's 154 MB (fp32
-// mode) read of G per layer and one pass over the S planes.
+// in ONE persistent tcgen05 kernel per layer.
 //
-// Warp roles (352 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two groups of four: group g
-// owns columns [32g, 32g+32) of every 64-column chunk and alternate 32-column pieces of g_s), warp 10 sends every
-// finished d tile to the G planes with ONE tensor store per plane (cp.async.bulk.tensor from the swizzled operand tile):
-// the epilogue threads issue no global stores for G (a thread-per-row store touches 32 cache lines per instruction — the
-// three-launch form's forward kernel is bound by exactly that), and the chunk's critical path is only
-// TMEM load -> subtract -> shared-memory store -> fence -> arrive.  The MMA thread issues forward and dgrad chunks in
-// whichever order their inputs become ready (W ring slot loaded / d tile written).
-// TMEM (512 columns): Y chunk double-buffered (2 x 64) + g_s double-buffered (2 x 192).
-// Shared memory, P = 2 planes (fp32 parity mode): S 96 KB + W ring 2 x 48 KB + d tile 32 KB = 224 KB;
-//                P = 1 (bf16): S 48 KB + W ring 4 x 24 KB + d tile 16 KB = 160 KB.
+// Per 128-row tile:
+//   * the S tile (student rows as bf16 hi / lo planes) is the A operand of the forward MMA and lives in TENSOR MEMORY
+//     (tcgen05.st by the epilogue threads, lane = row, a column = two consecutive K elements; tcgen05.mma reads A from TMEM):
+//     no shared memory and no shared-memory bandwidth for it — with S in shared memory (96 KB in the fp32 mode) only two W
+//     ring slots fit and every chunk exposed a full TMA round trip, and the 64-wide forward MMAs re-read the 4 KB A slice
+//     from shared memory per instruction (192 B/clk against the 128 B/clk the SM has);
+//   * W streams through a 4-slot ring in 64-row chunks of the teacher width (Dt), and the SAME chunk is used twice: K-major
+//     as the B operand of the forward MMA (Y_c = S W_c^T, K = Ds) and MN-major as the B operand of the dgrad MMA
+//     (g_s += d_c W_c, K = the chunk's 64 teacher channels);
+//   * the residual chunk d_c goes TMEM -> registers (teacher subtracted, loss accumulated) -> a 128-byte-swizzled K-major
+//     shared-memory tile that is both the A operand of dgrad and the source of ONE tensor store per plane into the G planes
+//     (no per-thread global stores for G); the g_s accumulator (128 x 192 fp32) stays in TMEM across the six chunks.
+// Compared with the three-launch form (forward, dgrad, wgrad) the dgrad kernel's read of G (154 MB per layer in the fp32
+// mode) and one pass over the S planes are gone.
+//
+// Warp roles (352 threads): warp 0 TMA producer (W ring), warp 1 MMA issuer (forward chunk c, then dgrad of chunk c-1),
+// warps 2-9 epilogue (two groups of four: group g owns columns [32g, 32g+32) of every chunk,
+// its share of the S tile, and alternate 32-column pieces of g_s), warp 10 G tensor stores.
+// TMEM (512 columns): Y chunk double-buffered (2 x 64) | g_s (192) | S planes (2 x 96).
+// Shared memory: W ring 4 x 48 KB + d tile 32 KB = 224 KB (fp32 mode, P = 2 planes); 4 x 24 + 16 = 112 KB (bf16, P = 1).
 #pragma once
 #include <stdlib.h>
+
 #include "epilogues.cuh"
 
 namespace dkd {
@@ -34,26 +38,24 @@ struct AlignFusedCfg {
   static constexpr int DS = 192, DT = 384, CH = 64;   // student width, teacher width, teacher channels per chunk
   static constexpr int NCH = DT / CH;                 // 6 chunks per tile
   static constexpr int KB = DS / 64;                  // 3 K blocks of the forward GEMM
-  static constexpr int WST = P_ == 2 ? 2 : 4;         // W ring stages
-  static constexpr int S_PLANE = KB * 128 * 128;      // 48 KB: [KB][128 rows][128 B]
+  static constexpr int WST = 4;                       // W ring slots
   static constexpr int W_PLANE = KB * CH * 128;       // 24 KB: [KB][64 rows][128 B]
   static constexpr int D_PLANE = 128 * 128;           // 16 KB: [128 rows][64 k]
-  static constexpr int S_BYTES = P_ * S_PLANE, W_STAGE = P_ * W_PLANE, D_BYTES = P_ * D_PLANE;
+  static constexpr int W_STAGE = P_ * W_PLANE, D_BYTES = P_ * D_PLANE;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32;   // + the G-store warp
-  static constexpr int NBARS = 2 + 2 * WST + 4 + 2 + 4;
-  static constexpr size_t SMEM = (size_t)S_BYTES + (size_t)WST * W_STAGE + D_BYTES + 1024 + 256;
-  static constexpr uint32_t TM_Y = 0, TM_GS = 128;    // TMEM column offsets
+  static constexpr size_t SMEM = (size_t)WST * W_STAGE + D_BYTES + 1024 + 256;
+  static constexpr uint32_t TM_Y = 0, TM_GS = 128, TM_S = 320;   // TMEM column offsets; S plane pl at TM_S + 96 * pl
+  static constexpr int S_COLS = DS / 2;               // 96 packed columns per plane
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 struct AlignFusedParams {
-  CUtensorMap tmS;        // S planes [P][M][192], box {64, 128, 1}
   CUtensorMap tmW;        // W planes [P][384][192], box {64, 64, 1}
   CUtensorMap tmG;        // G planes [P][M][384], box {64, 128, 1} (stores)
+  const __nv_bfloat16* S; // student planes [P][M][192]
   const void* t;          // teacher [B, Tt, 384]
   const float* bias;      // [384] or null
-  __nv_bfloat16* G;       // planes [P][M][384]
   void* g_s;              // [B, Ts, 192] dtype, or null
   double* partials;       // [gridDim.x]
   int64_t M;
@@ -62,8 +64,6 @@ struct AlignFusedParams {
   float gscale;           // G = gscale * d
   float gs_alpha;         // g_s = gs_alpha * (G W)
   int m_tiles;
-  int debug_skip;         // timing experiments only (DKD_FUSED_DEBUG bit mask; results are then WRONG): 1 no G store, 2 no teacher
-                          // loads, 4 no g_s stores, 8 no dgrad MMAs, 16 no forward MMAs
 };
 
 template <class Cfg>
@@ -71,34 +71,30 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
   using namespace sm100;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sS = smem;
-  uint8_t* sW = sS + Cfg::S_BYTES;
+  uint8_t* sW = smem;
   uint8_t* sD = sW + (size_t)Cfg::WST * Cfg::W_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + Cfg::D_BYTES);
-  uint64_t* s_full = bars;
-  uint64_t* s_empty = bars + 1;
+  uint64_t* s_full = bars;                    // S tile stored to TMEM (8 epilogue warps)
+  uint64_t* s_empty = bars + 1;               // last forward MMA of the tile retired
   uint64_t* w_full = bars + 2;
   uint64_t* w_empty = w_full + Cfg::WST;
   uint64_t* y_full = w_empty + Cfg::WST;      // [2]
   uint64_t* y_empty = y_full + 2;             // [2]
   uint64_t* d_full = y_empty + 2;
   uint64_t* d_empty = d_full + 1;
-  uint64_t* gs_full = d_empty + 1;            // [2]
-  uint64_t* gs_empty = gs_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gs_empty + 2);
+  uint64_t* gs_full = d_empty + 1;
+  uint64_t* gs_empty = gs_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gs_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    mbar_init(s_full, 1); mbar_init(s_empty, 1);
+    mbar_init(s_full, Cfg::EPI_WARPS); mbar_init(s_empty, 1);
     for (int s = 0; s < Cfg::WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&y_full[a], 1); mbar_init(&y_empty[a], Cfg::EPI_WARPS);
-      mbar_init(&gs_full[a], 1); mbar_init(&gs_empty[a], Cfg::EPI_WARPS);
-    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&y_full[a], 1); mbar_init(&y_empty[a], Cfg::EPI_WARPS); }
     mbar_init(d_full, Cfg::EPI_WARPS); mbar_init(d_empty, 2);   // d tile free = dgrad MMAs retired + tensor store has read it
+    mbar_init(gs_full, 1); mbar_init(gs_empty, Cfg::EPI_WARPS);
     fence_barrier_init();
-    tma_prefetch_desc(&p.tmS);
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmG);
   }
@@ -109,17 +105,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producer: W chunks ==============================
     if (lane == 0) {
-      uint32_t ti = 0, wi = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++ti) {
-        mbar_wait(s_empty, (ti & 1) ^ 1);
-        mbar_expect_tx(s_full, Cfg::S_BYTES);
-#pragma unroll
-        for (int pl = 0; pl < Cfg::P; ++pl)
-#pragma unroll
-          for (int kb = 0; kb < Cfg::KB; ++kb)
-            tma_load_3d(sS + (size_t)pl * Cfg::S_PLANE + (size_t)kb * 128 * 128, &p.tmS, s_full, kb * 64, tile * 128, pl);
+      uint32_t wi = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         for (int c = 0; c < Cfg::NCH; ++c, ++wi) {
           const int ws = wi % Cfg::WST;
           mbar_wait(&w_empty[ws], ((wi / Cfg::WST) & 1) ^ 1);
@@ -135,79 +124,73 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop (barrier waits by all 32 lanes, warp-uniform addresses) and one elected lane issues the
+    // tcgen05 instructions: inside an `if (lane == 0)` region every descriptor is a per-thread value and ptxas moves it to
+    // the uniform datapath with an ELECT / R2UR / BRA.U.ANY loop per operand (~13 instructions and several dependent
+    // uniform-pipe latencies per MMA) — more than the 32 tensor cycles of a 128 x 64 x 16 MMA, i.e. the issue thread, not
+    // the tensor pipe, paced the 64-column forward chunks.
+    {
       constexpr uint32_t idesc_f = make_idesc_bf16(128, Cfg::CH, MAJOR_K, MAJOR_K);     // Y_c[128, 64] = S[128, 192] W_c[64, 192]^T
       constexpr uint32_t idesc_d = make_idesc_bf16(128, Cfg::DS, MAJOR_K, MAJOR_MN);    // g_s[128, 192] += d_c[128, 64] W_c[64, 192]
       uint32_t ti = 0, ci = 0;     // tiles / chunks processed by this CTA
-      // dgrad of chunk `cd` (global chunk counter) of the current tile into g_s buffer `gsb`; `first` = chunk 0 of its tile
-      auto dgrad = [&](uint32_t cd, uint32_t gsb, bool first) {
+      const uint32_t sW_base = smem_u32(sW), sD_base = smem_u32(sD);
+      // dgrad of global chunk `cd` (tile-local index `d`): needs the d tile from the epilogue; chunk 0 also needs the
+      // previous tile's g_s rows read out of tensor memory
+      auto dgrad = [&](uint32_t cd, int d, uint32_t ti_) {
         const int ws = cd % Cfg::WST;
+        mbar_wait(d_full, cd & 1);
+        if (d == 0) mbar_wait(gs_empty, (ti_ & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = smem_u32(sD), w_addr = smem_u32(sW + (size_t)ws * Cfg::W_STAGE);
-        const uint32_t t_gs = tmem_base + Cfg::TM_GS + gsb * Cfg::DS;
+        if (elect_one()) {
+          const uint32_t w_addr = sW_base + ws * Cfg::W_STAGE;
+          const uint32_t t_gs = tmem_base + Cfg::TM_GS;
 #pragma unroll
-        for (int term = 0; term < Cfg::TERMS; ++term) {
-          const uint32_t a_pl = d_addr + (Cfg::P == 2 && term == 1 ? Cfg::D_PLANE : 0);
-          const uint32_t b_pl = w_addr + (Cfg::P == 2 && term == 0 ? Cfg::W_PLANE : 0);
-          if (p.debug_skip & 8) continue;
+          for (int term = 0; term < Cfg::TERMS; ++term) {
+            const uint32_t a_pl = sD_base + (Cfg::P == 2 && term == 1 ? Cfg::D_PLANE : 0);
+            const uint32_t b_pl = w_addr + (Cfg::P == 2 && term == 0 ? Cfg::W_PLANE : 0);
 #pragma unroll
-          for (int k = 0; k < Cfg::CH / 16; ++k)
-            umma_bf16(t_gs, kmajor_desc(a_pl + k * 32), mnmajor_desc(b_pl + k * 2048, Cfg::CH * 128), idesc_d,
-                      (first && term == 0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < Cfg::CH / 16; ++k)
+              umma_bf16(t_gs, kmajor_desc(a_pl + k * 32), mnmajor_desc(b_pl + k * 2048, Cfg::CH * 128), idesc_d,
+                        (d == 0 && term == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit(d_empty);          // the d tile may be rewritten ...
+          umma_commit(&w_empty[ws]);     // ... and the W chunk's ring slot refilled once these MMAs retire
         }
-        umma_commit(d_empty);          // the d tile may be rewritten ...
-        umma_commit(&w_empty[ws]);     // ... and the W chunk's ring slot refilled once these MMAs retire
+        __syncwarp();
       };
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++ti) {
-        const uint32_t gsb = ti & 1;
         mbar_wait(s_full, ti & 1);
-        mbar_wait(&gs_empty[gsb], ((ti >> 1) & 1) ^ 1);
-        tc_fence_after();
-        // Forward chunk f needs its W ring slot loaded and a free Y buffer; dgrad chunk d needs the d tile of chunk d from
-        // the epilogue.  Whichever is ready goes first (forward preferred: it feeds the epilogue): with two ring slots the
-        // W chunk c+2 can only be fetched once dgrad(c) has retired, and a fixed order would expose that fetch every chunk.
-        int f = 0, d = 0;
-        const uint32_t c0 = ci;                      // global index of this tile's chunk 0
-        const long long t_start = clock64();
-        while (d < Cfg::NCH) {
-          bool did = false;
-          if (f < Cfg::NCH) {
-            const uint32_t cf = c0 + f;
-            const int ws = cf % Cfg::WST;
-            const uint32_t yb = cf & 1;
-            if (mbar_try_wait(&w_full[ws], (cf / Cfg::WST) & 1) && mbar_try_wait(&y_empty[yb], ((cf >> 1) & 1) ^ 1)) {
-              tc_fence_after();
-              const uint32_t s_addr = smem_u32(sS), w_addr = smem_u32(sW + (size_t)ws * Cfg::W_STAGE);
-              const uint32_t t_y = tmem_base + Cfg::TM_Y + yb * Cfg::CH;
+        // forward chunk c, then dgrad of chunk c-1 (whose d tile the epilogue produces while forward c runs)
+#pragma unroll 1
+        for (int c = 0; c < Cfg::NCH; ++c, ++ci) {
+          const int ws = ci % Cfg::WST;
+          const uint32_t yb = ci & 1;
+          mbar_wait(&w_full[ws], (ci / Cfg::WST) & 1);
+          mbar_wait(&y_empty[yb], ((ci >> 1) & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t w_addr = sW_base + ws * Cfg::W_STAGE;
+            const uint32_t t_y = tmem_base + Cfg::TM_Y + yb * Cfg::CH;
 #pragma unroll
-              for (int term = 0; term < Cfg::TERMS; ++term) {
-                const uint32_t a_pl = s_addr + (Cfg::P == 2 && term == 1 ? Cfg::S_PLANE : 0);
-                const uint32_t b_pl = w_addr + (Cfg::P == 2 && term == 0 ? Cfg::W_PLANE : 0);
+            for (int term = 0; term < Cfg::TERMS; ++term) {      // (S plane, W plane): (hi, lo) (lo, hi) (hi, hi)
+              const uint32_t a_pl = tmem_base + Cfg::TM_S + (Cfg::P == 2 && term == 1 ? Cfg::S_COLS : 0);
+              const uint32_t b_pl = w_addr + (Cfg::P == 2 && term == 0 ? Cfg::W_PLANE : 0);
 #pragma unroll
-                for (int kb = 0; kb < Cfg::KB; ++kb)
+              for (int kb = 0; kb < Cfg::KB; ++kb)
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (!(p.debug_skip & 16)) umma_bf16(t_y, kmajor_desc(a_pl + kb * 128 * 128 + k * 32), kmajor_desc(b_pl + kb * Cfg::CH * 128 + k * 32), idesc_f,
-                              (term | kb | k) != 0 ? 1u : 0u);
-              }
-              umma_commit(&y_full[yb]);
-              if (f == Cfg::NCH - 1) umma_commit(s_empty);    // last forward MMA of the tile: the S planes may be replaced
-              ++f;
-              did = true;
+                for (int k = 0; k < 4; ++k)      // 16 K elements = 8 packed TMEM columns per instruction
+                  umma_bf16_ts(t_y, a_pl + kb * 32 + k * 8, kmajor_desc(b_pl + kb * Cfg::CH * 128 + k * 32), idesc_f,
+                               (term | kb | k) != 0 ? 1u : 0u);
             }
+            umma_commit(&y_full[yb]);
+            if (c == Cfg::NCH - 1) umma_commit(s_empty);    // last forward MMA of the tile: the S planes may be replaced
           }
-          if (!did && d < f && mbar_try_wait(d_full, (c0 + d) & 1)) {
-            dgrad(c0 + d, gsb, d == 0);
-            ++d;
-            did = true;
-          }
-          if (!did && clock64() - t_start > 4000000000ll) {
-            printf("dkd: fused align MMA issue timed out (block %d, f %d, d %d)\n", blockIdx.x, f, d);
-            __trap();
-          }
+          __syncwarp();
+          if (c >= 1) dgrad(ci - 1, c - 1, ti);
         }
-        ci += Cfg::NCH;
-        umma_commit(&gs_full[gsb]);
+        dgrad(ci - 1, Cfg::NCH - 1, ti);
+        if (elect_one()) umma_commit(gs_full);
+        __syncwarp();
       }
     }
   } else if (warp == 2 + Cfg::EPI_WARPS) {
@@ -219,12 +202,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         for (int c = 0; c < Cfg::NCH; ++c, ++ci) {
           mbar_wait(d_full, ci & 1);
-          if (!(p.debug_skip & 1)) {
 #pragma unroll
-            for (int pl = 0; pl < Cfg::P; ++pl) tma_store_3d(&p.tmG, sD + (size_t)pl * Cfg::D_PLANE, c * Cfg::CH, tile * 128, pl);
-            tma_store_commit();
-            tma_store_wait_read<0>();       // the store has read the tile
-          }
+          for (int pl = 0; pl < Cfg::P; ++pl) tma_store_3d(&p.tmG, sD + (size_t)pl * Cfg::D_PLANE, c * Cfg::CH, tile * 128, pl);
+          tma_store_commit();
+          tma_store_wait_read<0>();       // the store has read the tile
           mbar_arrive(d_empty);
         }
       }
@@ -239,6 +220,38 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
     float acc = 0.f;
     float ta[32], tb[32];
     uint32_t ti = 0, ci = 0;
+
+    // S tile of `tile_` -> tensor memory (lane = row, 96 packed columns per plane).  P = 2: group g stores plane g;
+    // P = 1: group 0 stores columns [0, 64), group 1 columns [64, 96).  The row's loads are issued first (one DRAM round
+    // trip), then the TMEM stores.
+    auto stage_S = [&](int tile_, uint32_t ti_) {
+      const int64_t m_ = (int64_t)tile_ * 128 + row_in_tile;
+      const bool live_ = m_ < p.M;
+      constexpr int NR = Cfg::P == 2 ? 96 : 64;                           // register words (P = 1, group 1 uses the first 32)
+      const int plane = Cfg::P == 2 ? group : 0;
+      const int col0 = Cfg::P == 2 ? 0 : group * 64;                      // first packed column of this thread's share
+      const int nw = Cfg::P == 2 ? 96 : (group ? 32 : 64);
+      uint32_t r[NR];
+      const uint4* src = reinterpret_cast<const uint4*>(p.S + (int64_t)plane * p.M * Cfg::DS + (live_ ? m_ : 0) * Cfg::DS + 2 * col0);
+#pragma unroll
+      for (int q = 0; q < NR / 4; ++q) {
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (live_ && 4 * q < nw) w = __ldg(src + q);
+        r[4 * q] = w.x; r[4 * q + 1] = w.y; r[4 * q + 2] = w.z; r[4 * q + 3] = w.w;
+      }
+      mbar_wait(s_empty, (ti_ & 1) ^ 1);      // the previous tile's forward MMAs have retired
+      tc_fence_after();
+      const uint32_t t_s = tmem_base + lane_base + Cfg::TM_S + plane * Cfg::S_COLS + col0;
+      tmem_st32(t_s, *reinterpret_cast<const uint32_t(*)[32]>(&r[0]));
+      if (Cfg::P == 2 || group == 0) tmem_st32(t_s + 32, *reinterpret_cast<const uint32_t(*)[32]>(&r[32]));
+      if constexpr (Cfg::P == 2) tmem_st32(t_s + 64, *reinterpret_cast<const uint32_t(*)[32]>(&r[64]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_full);
+    };
+
+    if ((int)blockIdx.x < p.m_tiles) stage_S(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++ti) {
       const int64_t m = (int64_t)tile * 128 + row_in_tile;
       const bool live = m < p.M;
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
       // hide); chunk c+1's values are requested before chunk c is processed, chunk 0 of the NEXT tile before this tile's
       // g_s rows are stored
       auto load_t = [&](int64_t trow_, bool live_, int col, float (&x)[32]) {
-        if (!live_ || (p.debug_skip & 2)) {
+        if (!live_) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = 0.f;
         } else {
@@ -302,8 +315,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
       };
       if (ti == 0) load_t(trow, live, group * 32, ta);      // later tiles: requested at the end of the previous tile
       // the next tile's row (for its chunk-0 prefetch)
-      const int64_t m_n = (int64_t)(tile + (int)gridDim.x) * 128 + row_in_tile;
-      const bool live_n = tile + (int)gridDim.x < p.m_tiles && m_n < p.M;
+      const int tile_n = tile + (int)gridDim.x;
+      const int64_t m_n = (int64_t)tile_n * 128 + row_in_tile;
+      const bool live_n = tile_n < p.m_tiles && m_n < p.M;
       const int64_t b_n = live_n ? m_n / p.n_tok : 0;
       const int64_t trow_n = b_n * p.Tt + p.t_off + (live_n ? m_n - b_n * p.n_tok : 0);
       static_assert(Cfg::NCH % 2 == 0, "chunks are processed in pairs");
@@ -315,31 +329,32 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
         else load_t(trow_n, live_n, group * 32, ta);
         chunk(c + 1, tb);
       }
+      // the next tile's S planes go to tensor memory BEFORE this tile's g_s rows are read out: its forward MMAs then run
+      // under the g_s stores (the last forward of this tile retired before y_full of chunk 5, so s_empty has completed)
+      if (tile_n < p.m_tiles) stage_S(tile_n, ti + 1);
       // ---- g_s rows of this tile: 6 pieces of 32 columns, alternating between the two groups
-      const uint32_t gsb = ti & 1;
-      mbar_wait(&gs_full[gsb], (ti >> 1) & 1);
+      mbar_wait(gs_full, ti & 1);
       tc_fence_after();
       const int64_t orow = b * p.Ts + p.s_off + tok;
 #pragma unroll 1
       for (int c0 = group * 32; c0 < Cfg::DS; c0 += 64) {
         float v[32];
-        tmem_ld32(tmem_base + lane_base + Cfg::TM_GS + gsb * Cfg::DS + c0, v);
+        tmem_ld32(tmem_base + lane_base + Cfg::TM_GS + c0, v);
         tmem_ld_wait();
-        if (!live || p.g_s == nullptr || (p.debug_skip & 4)) continue;
+        if (!live || p.g_s == nullptr) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= p.gs_alpha;
-        float z[32];
+        float z8[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) z[j] = 0.f;
+        for (int j = 0; j < 8; ++j) z8[j] = 0.f;
         if (p.out_is_bf16) {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.g_s) + orow * Cfg::DS + c0;
           stg256(op, *reinterpret_cast<float(*)[16]>(&v[0]));
           stg256(op + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
           if (tok == 0)      // the special-token rows in front of this sample's patches get zero gradient
-            for (int r = 1; r <= p.s_off; ++r) {
-              stg256(op - (int64_t)r * Cfg::DS, *reinterpret_cast<float(*)[16]>(&z[0]));
-              stg256(op - (int64_t)r * Cfg::DS + 16, *reinterpret_cast<float(*)[16]>(&z[16]));
-            }
+            for (int r = 1; r <= p.s_off; ++r)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) Vec<__nv_bfloat16, 8>::store(op - (int64_t)r * Cfg::DS + 8 * j, z8);
         } else {
           float* op = reinterpret_cast<float*>(p.g_s) + orow * Cfg::DS + c0;
 #pragma unroll
@@ -347,12 +362,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) align_fused_kernel(const __gr
           if (tok == 0)
             for (int r = 1; r <= p.s_off; ++r)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) stg256(op - (int64_t)r * Cfg::DS + 8 * j, *reinterpret_cast<float(*)[8]>(&z[8 * j]));
+              for (int j = 0; j < 4; ++j) stg256(op - (int64_t)r * Cfg::DS + 8 * j, z8);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&gs_empty[gsb]);
+      if (lane == 0) mbar_arrive(gs_empty);
     }
     epilogue_block_partial<Cfg::EPI_WARPS>(acc, threadIdx.x - 64, p.partials);
   }
@@ -372,16 +387,13 @@ inline int align_fused_fwd_dgrad_t(const __nv_bfloat16* S, const __nv_bfloat16* 
                                    int out_is_bf16, float gs_alpha, int64_t M, cudaStream_t st, int* grid_out, const char* what) {
   using Cfg = AlignFusedCfg<P>;
   AlignFusedParams p;
-  int rc = make_plane_tmap(&p.tmS, S, P, M, Cfg::DS, Cfg::DS, M * Cfg::DS, 128, what);
-  if (rc != DKD_OK) return rc;
-  rc = make_plane_tmap(&p.tmW, Wp, P, Cfg::DT, Cfg::DS, Cfg::DS, (int64_t)Cfg::DT * Cfg::DS, Cfg::CH, what);
+  int rc = make_plane_tmap(&p.tmW, Wp, P, Cfg::DT, Cfg::DS, Cfg::DS, (int64_t)Cfg::DT * Cfg::DS, Cfg::CH, what);
   if (rc != DKD_OK) return rc;
   rc = make_plane_tmap(&p.tmG, G, P, M, Cfg::DT, Cfg::DT, M * Cfg::DT, 128, what);
   if (rc != DKD_OK) return rc;
-  p.t = t; p.bias = bias; p.G = G; p.g_s = g_s; p.partials = partials; p.M = M; p.n_tok = n_tok; p.Tt = Tt; p.t_off = t_off;
+  p.S = S; p.t = t; p.bias = bias; p.g_s = g_s; p.partials = partials; p.M = M; p.n_tok = n_tok; p.Tt = Tt; p.t_off = t_off;
   p.Ts = Ts; p.s_off = s_off; p.t_is_bf16 = t_is_bf16; p.out_is_bf16 = out_is_bf16; p.gscale = gscale; p.gs_alpha = gs_alpha;
   p.m_tiles = (int)((M + 127) / 128);
-  { const char* e = getenv("DKD_FUSED_DEBUG"); p.debug_skip = e ? atoi(e) : 0; }
   const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;
   auto kern = align_fused_kernel<Cfg>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);

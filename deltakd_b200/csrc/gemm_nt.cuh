@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp walks the loop, one elected lane issues (see gemm_tn.cuh)
       constexpr uint32_t a_major = Cfg::A_KMAJOR ? MAJOR_K : MAJOR_MN;
       constexpr uint32_t idesc0 = make_idesc_bf16(128, Cfg::N0, a_major, MAJOR_MN);
       constexpr uint32_t idesc1 = make_idesc_bf16(128, Cfg::N1 > 0 ? Cfg::N1 : 16, a_major, MAJOR_MN);
@@ -161,22 +161,25 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           const uint32_t a_st = smem_u32(sA + (size_t)s * A_STAGE);
           const uint32_t b_st = smem_u32(sB + (size_t)s * B_STAGE);
           constexpr int TERMS = Cfg::PLANES == 2 ? 3 : 1;     // (A plane, B plane): (hi,lo) (lo,hi) (hi,hi)
+          if (elect_one()) {
 #pragma unroll
-          for (int term = 0; term < TERMS; ++term) {
-            const uint32_t a_addr = a_st + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
-            const uint32_t b_addr = b_st + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
+            for (int term = 0; term < TERMS; ++term) {
+              const uint32_t a_addr = a_st + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
+              const uint32_t b_addr = b_st + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
 #pragma unroll
-            for (int k = 0; k < Cfg::KSTEPS; ++k) {  // UMMA_K = 16 rows = 2 groups of 8 rows = 2048 B
-              const uint64_t da = Cfg::A_KMAJOR ? kmajor_desc(a_addr + k * 32) : mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
-              umma_bf16(tmem_base, da, mnmajor_desc(b_addr + k * 2048, Cfg::BOX_BYTES), idesc0, (kit | term | k) != 0 ? 1u : 0u);
-              if constexpr (Cfg::N1 > 0)
-                umma_bf16(tmem_base + Cfg::N0, da, mnmajor_desc(b_addr + (Cfg::N0 / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES),
-                          idesc1, (kit | term | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < Cfg::KSTEPS; ++k) {  // UMMA_K = 16 rows = 2 groups of 8 rows = 2048 B
+                const uint64_t da = Cfg::A_KMAJOR ? kmajor_desc(a_addr + k * 32) : mnmajor_desc(a_addr + k * 2048, Cfg::BOX_BYTES);
+                umma_bf16(tmem_base, da, mnmajor_desc(b_addr + k * 2048, Cfg::BOX_BYTES), idesc0, (kit | term | k) != 0 ? 1u : 0u);
+                if constexpr (Cfg::N1 > 0)
+                  umma_bf16(tmem_base + Cfg::N0, da, mnmajor_desc(b_addr + (Cfg::N0 / 64) * Cfg::BOX_BYTES + k * 2048, Cfg::BOX_BYTES),
+                            idesc1, (kit | term | k) != 0 ? 1u : 0u);
+              }
             }
+            if constexpr (Cfg::CLUSTER > 1) umma_commit_mc(&empty[s], kClusterMask);
+            else umma_commit(&empty[s]);
+            if (kit == nk - 1) umma_commit(acc_full);
           }
-          if constexpr (Cfg::CLUSTER > 1) umma_commit_mc(&empty[s], kClusterMask);
-          else umma_commit(&empty[s]);
-          if (kit == nk - 1) umma_commit(acc_full);
+          __syncwarp();
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
         aph ^= 1;
@@ -211,9 +214,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(drow + c0 + j) =
                 make_float4(v[j] * p.ep.alpha, v[j + 1] * p.ep.alpha, v[j + 2] * p.ep.alpha, v[j + 3] * p.ep.alpha);
-        } else {
+        } else {   // split-K reduction: 128-bit vector reductions (REDG.ADD.F32x4): a quarter of the L2 atomic operations
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j] * p.ep.alpha);
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + j), "f"(v[j] * p.ep.alpha),
+                         "f"(v[j + 1] * p.ep.alpha), "f"(v[j + 2] * p.ep.alpha), "f"(v[j + 3] * p.ep.alpha)
+                         : "memory");
         }
       }
       if constexpr (Cfg::ONES) {

@@ -118,7 +118,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform addresses stay on the uniform datapath) and one elected lane issues:
+    // under `if (lane == 0)` every descriptor is a per-thread value that ptxas moves to uniform registers with an
+    // ELECT / R2UR / BRA.U.ANY loop — ~13 instructions per MMA instead of 1-3.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, Cfg::N_INSTR, MAJOR_K, MAJOR_K);
       int s = 0; uint32_t ph = 0;
       int a = 0; uint32_t aph = 0;
@@ -132,23 +135,26 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
           const uint32_t a_addr = smem_u32(sA + (size_t)s * A_STAGE);
           const uint32_t b_addr = smem_u32(sB + (size_t)s * B_STAGE);
           constexpr int TERMS = Cfg::PLANES == 2 ? 3 : 1;     // (A plane, B plane): (hi,lo) (lo,hi) (hi,hi) — small terms first
+          if (elect_one()) {
 #pragma unroll
-          for (int term = 0; term < TERMS; ++term) {
-            const uint32_t a_pl = a_addr + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
-            const uint32_t b_pl = b_addr + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
+            for (int term = 0; term < TERMS; ++term) {
+              const uint32_t a_pl = a_addr + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
+              const uint32_t b_pl = b_addr + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
 #pragma unroll
-            for (int k = 0; k < Cfg::BK / 16; ++k) {
-              const uint64_t da = kmajor_desc(a_pl + k * 32);
+              for (int k = 0; k < Cfg::BK / 16; ++k) {
+                const uint64_t da = kmajor_desc(a_pl + k * 32);
 #pragma unroll
-              for (int ni = 0; ni < Cfg::NI; ++ni) {
-                const uint64_t db = kmajor_desc(b_pl + ni * Cfg::N_INSTR * 128 + k * 32);
-                umma_bf16(d_tmem + ni * Cfg::N_INSTR, da, db, idesc, (kit | term | k) != 0 ? 1u : 0u);
+                for (int ni = 0; ni < Cfg::NI; ++ni) {
+                  const uint64_t db = kmajor_desc(b_pl + ni * Cfg::N_INSTR * 128 + k * 32);
+                  umma_bf16(d_tmem + ni * Cfg::N_INSTR, da, db, idesc, (kit | term | k) != 0 ? 1u : 0u);
+                }
               }
             }
+            if constexpr (Cfg::CLUSTER > 1) umma_commit_mc(&empty[s], kClusterMask);   // ... in every CTA of the cluster
+            else umma_commit(&empty[s]);                  // ring slot reusable once these MMAs retire
+            if (kit == num_k - 1) umma_commit(&acc_full[a]);  // accumulator complete
           }
-          if constexpr (Cfg::CLUSTER > 1) umma_commit_mc(&empty[s], kClusterMask);   // ... in every CTA of the cluster
-          else umma_commit(&empty[s]);                  // ring slot reusable once these MMAs retire
-          if (kit == num_k - 1) umma_commit(&acc_full[a]);  // accumulator complete
+          __syncwarp();
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
         if (++a == Cfg::ACC) { a = 0; aph ^= 1; }

@@ -160,6 +160,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 consecutive 32-bit columns of this thread's TMEM lane <- registers (the mirror of tmem_ld32); used to stage an MMA
+// A operand in tensor memory: lane = row, a column holds two consecutive K elements (bf16 pair)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- tcgen05.mma ------------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.  accumulate == 0 overwrites D.
@@ -169,6 +182,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t desc_a, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 per instruction = 8 columns) is read from tensor
+// memory instead of shared memory — no shared-memory bandwidth for A, and its shared-memory tile is not needed.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on `bar` once every previously issued tcgen05.mma of this thread has completed
