@@ -63,8 +63,8 @@ def _f16_up_list(ts):
 _WS: dict = {}
 
 
-def _workspace(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
-    key = (device.index, _stream(), tag)
+def _workspace(device: torch.device, tag: str, nbytes: int, stream: int | None = None) -> torch.Tensor:
+    key = (device.index, _stream() if stream is None else stream, tag)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1024), dtype=torch.uint8, device=device)
@@ -146,10 +146,11 @@ class _LogitKD(torch.autograd.Function):
         g0 = torch.empty_like(outputs) if need_g0 else None
         g1 = torch.empty_like(outputs_kd) if need_g1 else None
         loss3 = torch.empty(3, dtype=torch.float32, device=ref.device)
-        ws = _workspace(ref.device, "logit_kd", _logit_ws_bytes(B))
+        st = _stream()
+        ws = _workspace(ref.device, "logit_kd", _logit_ws_bytes(B), st)
         rc = _LOGIT_FN(_ptr(outputs), _ptr(outputs_kd), _ptr(teacher_logits), _ptr(labels),
                        label_kind, kd_kind, B, Cn, dt, float(smoothing), float(alpha), float(tau), _ptr(mix_lam),
-                       _ptr(g0), _ptr(g1), loss3.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+                       _ptr(g0), _ptr(g1), loss3.data_ptr(), ws.data_ptr(), ws.numel(), st)
         if rc:
             _lib.check(rc, "dkd_logit_kd_fwdbwd")
         ctx.grads = (g0, g1)
@@ -163,6 +164,9 @@ class _LogitKD(torch.autograd.Function):
         return _rescale_(grad_total, g0, g1) + (None,) * 9
 
 
+_KD_KINDS = {"none": 0, "soft": 1, "hard": 2}
+
+
 def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, smoothing: float = 0.1,
                   alpha: float = 0.0, tau: float = 1.0, return_parts: bool = False, mix_lam=None):
     """Fused base CE (+ soft / hard KD) on logits.
@@ -173,11 +177,14 @@ def logit_kd_loss(outputs, outputs_kd, teacher_logits, labels, *, kd_kind: str, 
     lam*smooth_onehot(labels[r]) + (1-lam)*smooth_onehot(labels[B-1-r]), generated inside the kernel.
     Returns the 0-dim fp32 total `base*(1-alpha) + kd*alpha` (or base alone for "none").
     """
-    kk = {"none": 0, "soft": 1, "hard": 2}[kd_kind]
-    outputs, outputs_kd, teacher_logits = _f16_up(outputs), _f16_up(outputs_kd), _f16_up(teacher_logits)
-    if labels is not None and labels.dtype == torch.float16:
-        labels = labels.float()
+    kk = _KD_KINDS[kd_kind]
     ref = outputs if outputs is not None else outputs_kd
+    if ref.dtype == torch.float16 or (teacher_logits is not None and teacher_logits.dtype == torch.float16) or \
+            (labels is not None and labels.dtype == torch.float16):   # the reference's --amp path: exact upcast, see _f16_up
+        outputs, outputs_kd, teacher_logits = _f16_up(outputs), _f16_up(outputs_kd), _f16_up(teacher_logits)
+        if labels is not None and labels.dtype == torch.float16:
+            labels = labels.float()
+        ref = outputs if outputs is not None else outputs_kd
     _require_cuda(outputs, outputs_kd, teacher_logits, labels)
     if ref.dim() != 2:
         raise ValueError(f"logits must be [B, C], got {tuple(ref.shape)}")

@@ -20,6 +20,7 @@ import torch.nn as nn
 from . import functional as Fn
 from .features import forward_with_features, needed_layers, unwrap
 from .misc import len_keep_of, saliency_scores
+from .mixup import MixedLabels
 
 _FEATURE_TYPES = ("vitkd", "lrkd", "diffkd", "curkd", "saliency_mgd", "wasskd", "mgd")
 
@@ -27,7 +28,8 @@ _FEATURE_TYPES = ("vitkd", "lrkd", "diffkd", "curkd", "saliency_mgd", "wasskd", 
 def _labels_args(labels, smoothing):
     """(labels tensor, smoothing, mix_lam) for the fused logit kernel: `MixedLabels` (deltakd_b200.mixup) carry int64 ids +
     lam and the kernel builds timm's mixed soft label itself."""
-    from .mixup import MixedLabels
+    if isinstance(labels, torch.Tensor):
+        return labels, smoothing, None
     if isinstance(labels, MixedLabels):
         return labels.target, labels.smoothing, labels.lam
     return labels, smoothing, None
