@@ -953,6 +953,24 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
     if hasattr(w, "extra_info"):
         res.update(w.extra_info())
         res["img_per_s_per_gpu"] = w.B * K / (ms * 1e-3)
+        table = os.environ.get("DKD_BENCH_KERNEL_TABLE")
+        if table:   # evidence helper: per-kernel device times of 3 more steps (CUPTI through torch.profiler; all ranks step,
+            #         rank 0 records) — names the NCCL all-reduce kernel and its share of the step; never a bench number
+            from torch.profiler import ProfilerActivity, profile
+            barrier()
+            if w.rank == 0:
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    for i in range(3):
+                        w.step(dsets[i % nsets])
+                    torch.cuda.synchronize()
+                with open(f"{table}_{w.name}_n{world}.txt", "w") as fh:
+                    fh.write(f"# {w.name}, {world} rank(s), 3 steps on rank 0 (torch.profiler / CUPTI); step = {ms / K:.3f} ms (max over ranks)\n")
+                    fh.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
+            else:
+                for i in range(3):
+                    w.step(dsets[i % nsets])
+                torch.cuda.synchronize()
+            barrier()
     if with_cpu:
         res["cpu_baseline"] = cpu_baseline(w, budget_s=12.0 if isinstance(w, LogitKD) else 6.0)
     del dsets, host

@@ -71,7 +71,7 @@ inline int align_forward_residual_t(const __nv_bfloat16* S, const __nv_bfloat16*
 
 template <class Cfg>
 inline int align_dgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* g_s, int64_t M, int n_tok, int Ts, int s_off, int Ds, int Dt,
-                         int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what) {
+                         int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what, int g_lo_zero = 0) {
   using L = PlaneLoader<Cfg>;
   using E = StoreRowsEpi<Cfg>;
   GemmParams<L, E> p;
@@ -80,6 +80,7 @@ inline int align_dgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* 
   rc = make_plane_tmap(&p.ld.tmB, Wt, P, Ds, Dt, Dt, (int64_t)Dt * Ds, Cfg::BN, what);
   if (rc != DKD_OK) return rc;
   p.ld.k_blocks = Dt / 64; p.ld.nterms = P == 2 ? 3 : 1;
+  p.a_lo_zero = p.ld.a_lo_zero = (Cfg::PLANES == 2 && g_lo_zero) ? 1 : 0;
   p.ep.out = g_s; p.ep.drop_mask = nullptr; p.ep.bias = nullptr; p.ep.alpha = alpha;
   p.ep.M = M; p.ep.N_total = Ds; p.ep.n_tok = n_tok; p.ep.T_out = Ts; p.ep.off = s_off; p.ep.out_is_bf16 = out_is_bf16;
   p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM); p.n_tiles = Ds / Cfg::BN;
@@ -103,15 +104,16 @@ inline int align_forward_residual(const __nv_bfloat16* S, const __nv_bfloat16* W
                 : align_forward_residual_t<AlignCfg1>(S, Wp, bias, t, t_is_bf16, Tt, t_off, n_tok, G, partials, gscale, M, Ds, Dt, P, st,
                                                       grid_out, what);
 }
+// g_lo_zero: the lo plane of G is identically zero and is neither read nor multiplied (WassKD's +-1 gradient plane)
 inline int align_dgrad(const __nv_bfloat16* G, const __nv_bfloat16* Wt, void* g_s, int64_t M, int n_tok, int Ts, int s_off, int Ds, int Dt,
-                       int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what) {
-  return P == 2 ? align_dgrad_t<AlignCfg2>(G, Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, out_is_bf16, alpha, st, what)
+                       int P, int out_is_bf16, float alpha, cudaStream_t st, const char* what, int g_lo_zero = 0) {
+  return P == 2 ? align_dgrad_t<AlignCfg2>(G, Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, out_is_bf16, alpha, st, what, g_lo_zero)
                 : align_dgrad_t<AlignCfg1>(G, Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, out_is_bf16, alpha, st, what);
 }
 
 template <class Cfg>
 inline int align_wgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bfloat16* ones, float* g_W, float* g_b, int64_t M, int Ds, int Dt,
-                         int P, float alpha, cudaStream_t st, const char* what) {
+                         int P, float alpha, cudaStream_t st, const char* what, int g_lo_zero = 0) {
   using L = NtPlainLoader<Cfg>;
   GemmNtParamsT<Cfg, L> p;
   int rc = make_plane_tmap(&p.ld.tmA, G, P, M, Dt, Dt, M * Dt, Cfg::KROWS, what);
@@ -128,6 +130,7 @@ inline int align_wgrad_t(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bf
   p.ld.ldd = Ds; p.ld.na_tiles = Dt / 128; p.ld.b_col0 = 0;
   p.ld.total_row_blocks = (int)((M + Cfg::KROWS - 1) / Cfg::KROWS);
   p.nterms = P == 2 ? 3 : 1;
+  p.a_lo_zero = (Cfg::PLANES == 2 && g_lo_zero) ? 1 : 0;
   if constexpr (Cfg::CLUSTER > 1) {
     static const int resident = [] {
       auto kern = gemm_nt_kernel<Cfg, L>;
@@ -150,11 +153,11 @@ inline int align_wgrad_cluster() {
 }
 
 inline int align_wgrad(const __nv_bfloat16* G, const __nv_bfloat16* S, __nv_bfloat16* ones, float* g_W, float* g_b, int64_t M, int Ds, int Dt,
-                       int P, float alpha, cudaStream_t st, const char* what) {
+                       int P, float alpha, cudaStream_t st, const char* what, int g_lo_zero = 0) {
   if (align_wgrad_cluster() == 3 && Dt == 384)
-    return P == 2 ? align_wgrad_t<AlignWgradCfg2C>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what)
+    return P == 2 ? align_wgrad_t<AlignWgradCfg2C>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what, g_lo_zero)
                   : align_wgrad_t<AlignWgradCfg1C>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what);
-  return P == 2 ? align_wgrad_t<AlignWgradCfg2>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what)
+  return P == 2 ? align_wgrad_t<AlignWgradCfg2>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what, g_lo_zero)
                 : align_wgrad_t<AlignWgradCfg1>(G, S, ones, g_W, g_b, M, Ds, Dt, P, alpha, st, what);
 }
 

@@ -68,6 +68,7 @@ struct GemmNtParamsT {
   typename Loader::Params ld;
   NtEpilogueParams ep;
   int nterms;
+  int a_lo_zero = 0;   // PLANES == 2: A's lo plane is identically zero: not fetched, (A lo, B hi) product skipped
 };
 
 template <class Cfg, class Loader>
@@ -115,14 +116,16 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
         if constexpr (Cfg::PLANES == 2) {
           for (int rb = it.rb0; rb < it.rb1; ++rb) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], Loader::TX_BYTES);
+            mbar_expect_tx(&full[s], Loader::TX_BYTES - (p.a_lo_zero ? Cfg::A_BYTES : 0));
+            const bool with_a_lo = !p.a_lo_zero;
             if constexpr (Cfg::CLUSTER > 1) {
-              Loader::issue_planes_cluster(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], crank);
+              Loader::issue_planes_cluster(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], crank, true);
               Loader::issue_planes_cluster(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES,
-                                           &full[s], crank);
+                                           &full[s], crank, with_a_lo);
             } else {
-              Loader::issue_planes(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
-              Loader::issue_planes(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES, &full[s]);
+              Loader::issue_planes(p.ld, it, 0, 0, rb, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], true);
+              Loader::issue_planes(p.ld, it, 1, 1, rb, sA + (size_t)s * A_STAGE + Cfg::A_BYTES, sB + (size_t)s * B_STAGE + Cfg::B_BYTES, &full[s],
+                                   with_a_lo);
             }
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
           }
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_kernel(const __grid_c
           if (elect_one()) {
 #pragma unroll
             for (int term = 0; term < TERMS; ++term) {
+              if (Cfg::PLANES == 2 && term == 1 && p.a_lo_zero) continue;
               const uint32_t a_addr = a_st + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
               const uint32_t b_addr = b_st + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
 #pragma unroll
@@ -324,9 +328,12 @@ struct NtPlainLoader {
     term_planes(term, nterms, pa, pb);
     issue_planes(p, it, pa, pb, rb, a, b, bar);
   }
-  static __device__ __forceinline__ void issue_planes(const Params& p, const Item& it, int pa, int pb, int rb, uint8_t* a, uint8_t* b, uint64_t* bar) {
-    sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
-    sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
+  static __device__ __forceinline__ void issue_planes(const Params& p, const Item& it, int pa, int pb, int rb, uint8_t* a, uint8_t* b, uint64_t* bar,
+                                                      bool with_a = true) {
+    if (with_a) {
+      sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
+      sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
+    }
 #pragma unroll
     for (int i = 0; i < Cfg::NB_BOXES; ++i)
       sm100::tma_load_3d(b + (size_t)i * Cfg::BOX_BYTES, &p.tmB, bar, it.b_col0 + i * 64, rb * Cfg::KROWS, pb);
@@ -346,10 +353,12 @@ struct NtPlainLoader {
     it.aux = 0;
   }
   static __device__ __forceinline__ void issue_planes_cluster(const Params& p, const Item& it, int pa, int pb, int rb, uint8_t* a, uint8_t* b,
-                                                              uint64_t* bar, int crank) {
+                                                              uint64_t* bar, int crank, bool with_a = true) {
     static_assert(Cfg::CLUSTER == 1 || Cfg::NB_BOXES == Cfg::CLUSTER, "one B box per CTA of the cluster");
-    sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
-    sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
+    if (with_a) {
+      sm100::tma_load_3d(a, &p.tmA, bar, it.a_col0, rb * Cfg::KROWS, pa);
+      sm100::tma_load_3d(a + Cfg::BOX_BYTES, &p.tmA, bar, it.a_col0 + 64, rb * Cfg::KROWS, pa);
+    }
     sm100::tma_load_3d_mc(b + (size_t)crank * Cfg::BOX_BYTES, &p.tmB, bar, it.b_col0 + crank * 64, rb * Cfg::KROWS, pb,
                           (uint16_t)((1u << Cfg::CLUSTER) - 1u));
     if constexpr (Cfg::ONES) sm100::tma_load_3d(b + (size_t)Cfg::NB_BOXES * Cfg::BOX_BYTES, &p.tmOnes, bar, 0, 0, pb);

@@ -60,6 +60,9 @@ struct GemmParams {
   typename Loader::Params ld;
   typename Epi::Params ep;
   int m_tiles, n_tiles;
+  // PLANES == 2 only: the A operand's lo plane is identically zero (e.g. a +-1 gradient plane): its loads and the
+  // (A lo, B hi) product are skipped — two products and a third less A traffic.  The loader honours `ld.a_lo_zero`.
+  int a_lo_zero = 0;
 };
 
 template <class Cfg, class Loader, class Epi>
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         for (int kit = 0; kit < num_k; ++kit) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], Loader::TX_BYTES);
+          mbar_expect_tx(&full[s], Loader::TX_BYTES - ((Cfg::PLANES == 2 && p.a_lo_zero) ? Cfg::A_BYTES : 0));
           if constexpr (Cfg::CLUSTER > 1) Loader::issue_cluster(p.ld, kit, mt, nt, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s], crank);
           else Loader::issue(p.ld, kit, mt, nt, sA + (size_t)s * A_STAGE, sB + (size_t)s * B_STAGE, &full[s]);
           if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
           if (elect_one()) {
 #pragma unroll
             for (int term = 0; term < TERMS; ++term) {
+              if (Cfg::PLANES == 2 && term == 1 && p.a_lo_zero) continue;
               const uint32_t a_pl = a_addr + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
               const uint32_t b_pl = b_addr + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
 #pragma unroll
@@ -262,6 +266,7 @@ struct PlaneLoaderParams {
   CUtensorMap tmA, tmB;
   int k_blocks;   // ceil(K / 64)
   int nterms;     // 1 or 3
+  int a_lo_zero = 0;   // PLANES == 2: do not fetch A's lo plane (see GemmParams::a_lo_zero)
 };
 template <class Cfg, int B_BOX_ROWS = (Cfg::BN > 256 ? Cfg::BN / 2 : Cfg::BN)>
 struct PlaneLoader {
@@ -276,7 +281,7 @@ struct PlaneLoader {
     if constexpr (Cfg::PLANES == 2) {       // both planes of both operands, once per K block
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
-        sm100::tma_load_3d(sA + (size_t)pl * Cfg::A_BYTES, &p.tmA, bar, kit * 64, mt * Cfg::BM, pl);
+        if (!(pl == 1 && p.a_lo_zero)) sm100::tma_load_3d(sA + (size_t)pl * Cfg::A_BYTES, &p.tmA, bar, kit * 64, mt * Cfg::BM, pl);
 #pragma unroll
         for (int i = 0; i < Cfg::BN / B_BOX_ROWS; ++i)
           sm100::tma_load_3d(sB + (size_t)pl * Cfg::B_BYTES + (size_t)i * B_BOX_ROWS * 128, &p.tmB, bar, kit * 64,

@@ -124,6 +124,12 @@ struct DiagParams {
   float scale;
 };
 
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(256) selfdiag_score_kernel(DiagParams p) {
   extern __shared__ float sm[];
   float* ks = sm;  // [n_tok][48]
@@ -145,10 +151,13 @@ __global__ void __launch_bounds__(256) selfdiag_score_kernel(DiagParams p) {
 #pragma unroll
     for (int c = 0; c < kHeadDim; c += 4) {
       const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * ld + h * kHeadDim + c);
-      q[c] = v.x * p.scale; q[c + 1] = v.y * p.scale; q[c + 2] = v.z * p.scale; q[c + 3] = v.w * p.scale;
+      const float sc = p.scale * 1.4426950408889634f;   // logits in base 2
+      q[c] = v.x * sc; q[c + 1] = v.y * sc; q[c + 2] = v.z * sc; q[c + 3] = v.w * sc;
     }
+    // online softmax in base 2 over groups of 4 keys: one rescale per group (branch-free), MUFU ex2 (relative error 2^-22,
+    // far inside the 1e-5 score gate); the logits carry log2(e) through the pre-scaled query
     float m = -INFINITY, l = 0.f, sii = 0.f;
-    for (int j = 0; j < p.n_tok; ++j) {
+    auto dot = [&](int j) {
       const float4* kr = reinterpret_cast<const float4*>(ks + j * kHeadDim);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -157,11 +166,24 @@ __global__ void __launch_bounds__(256) selfdiag_score_kernel(DiagParams p) {
         a0 = fmaf(q[4 * c], kv.x, a0); a1 = fmaf(q[4 * c + 1], kv.y, a1);
         a2 = fmaf(q[4 * c + 2], kv.z, a2); a3 = fmaf(q[4 * c + 3], kv.w, a3);
       }
-      const float s = (a0 + a1) + (a2 + a3);
-      if (j == i) sii = s;
-      if (s > m) { l = l * expf(m - s) + 1.f; m = s; } else { l += expf(s - m); }
+      return (a0 + a1) + (a2 + a3);
+    };
+    int j = 0;
+    for (; j + 4 <= p.n_tok; j += 4) {
+      const float s0 = dot(j), s1 = dot(j + 1), s2 = dot(j + 2), s3 = dot(j + 3);
+      sii = i == j ? s0 : i == j + 1 ? s1 : i == j + 2 ? s2 : i == j + 3 ? s3 : sii;
+      const float mn = fmaxf(fmaxf(m, fmaxf(s0, s1)), fmaxf(s2, s3));
+      l = l * ex2(m - mn) + ((ex2(s0 - mn) + ex2(s1 - mn)) + (ex2(s2 - mn) + ex2(s3 - mn)));
+      m = mn;
     }
-    total += expf(sii - m) / l;
+    for (; j < p.n_tok; ++j) {
+      const float s0 = dot(j);
+      sii = i == j ? s0 : sii;
+      const float mn = fmaxf(m, s0);
+      l = l * ex2(m - mn) + ex2(s0 - mn);
+      m = mn;
+    }
+    total += ex2(sii - m) / l;
   }
   if (live) p.score[(size_t)b * p.n_tok + i] = total / (float)p.H;
 }

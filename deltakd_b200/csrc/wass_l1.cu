@@ -34,10 +34,12 @@ constexpr int kSearchIlp = 4;
 __device__ __forceinline__ void bitonic256_oct(float (&key)[kPerLane], int sub) {
 #pragma unroll
   for (int k = 2; k <= 256; k <<= 1) {
-    const bool flip = k >= kPerLane && k < 256 && ((sub * kPerLane) & k) != 0;
+    // sign flips as multiplications by +-1 (exact): FMUL runs on the FMA pipe — the kernel is bound by the ALU pipe
+    // (FMNMX, selects and compares issue at half rate there; ncu: 70 % ALU-pipe active at 52 % issue utilisation)
+    const float sgn = (k >= kPerLane && k < 256 && ((sub * kPerLane) & k) != 0) ? -1.f : 1.f;
     if (k >= kPerLane && k < 256) {
 #pragma unroll
-      for (int r = 0; r < kPerLane; ++r) key[r] = flip ? -key[r] : key[r];
+      for (int r = 0; r < kPerLane; ++r) key[r] *= sgn;
     }
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -64,7 +66,7 @@ __device__ __forceinline__ void bitonic256_oct(float (&key)[kPerLane], int sub) 
     }
     if (k >= kPerLane && k < 256) {
 #pragma unroll
-      for (int r = 0; r < kPerLane; ++r) key[r] = flip ? -key[r] : key[r];
+      for (int r = 0; r < kPerLane; ++r) key[r] *= sgn;
     }
   }
 }
@@ -72,7 +74,7 @@ __device__ __forceinline__ void bitonic256_oct(float (&key)[kPerLane], int sub) 
 struct SortParams {
   const float* a;        // [M, N] fp32 aligned student (scratch)
   const void* t;         // teacher [B, Tt, N]
-  __nv_bfloat16* G;      // [P][M][N] : plane 0 = sign(diff) in {-1,0,+1}, plane 1 (if any) = 0
+  __nv_bfloat16* G;      // [M][N] sign(diff) in {-1, 0, +1} (exact in bf16: the GEMMs that consume it skip the lo plane)
   double* partials;      // [gridDim]
   int64_t M;
   int N, n_tok, Tt, t_off, planes, t_is_bf16, write_grad, pitch;
@@ -294,7 +296,7 @@ int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float
   {
     SortParams sp;
     sp.a = ws.A; sp.t = t; sp.G = ws.G; sp.partials = ws.partials; sp.M = M; sp.N = Dt; sp.n_tok = n_tok; sp.Tt = Tt;
-    sp.t_off = t_off; sp.planes = P; sp.t_is_bf16 = dtype == DKD_BF16; sp.write_grad = want_grads;
+    sp.t_off = t_off; sp.planes = 1; sp.t_is_bf16 = dtype == DKD_BF16; sp.write_grad = want_grads;   // +-1 is exact in bf16: no lo plane
     sp.pitch = kMaxTok + 8;   // all 256 sorted slots (+inf padded) are stored; 264 = 8 mod 32: a warp's 4 columns gather from 32 banks
     const size_t sort_smem = (size_t)3 * kCh * sp.pitch * sizeof(float);
     cudaFuncSetAttribute(wass_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
@@ -307,12 +309,12 @@ int dkd_wass_l1_fwdbwd(const void* s, const void* t, const float* W, const float
   if (!want_grads) return DKD_OK;
 
   if (g_s) {  // g_s = scale * G W
-    rc = align_dgrad(ws.G, ws.Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, dtype == DKD_BF16, scale, st, "dkd_wass_l1_fwdbwd: dgrad GEMM");
+    rc = align_dgrad(ws.G, ws.Wt, g_s, M, n_tok, Ts, s_off, Ds, Dt, P, dtype == DKD_BF16, scale, st, "dkd_wass_l1_fwdbwd: dgrad GEMM", 1);
     if (rc != DKD_OK) return rc;
   }
   if (g_W || g_b) {
     DKD_REQUIRE(g_W != nullptr, DKD_E_UNSUPPORTED, "%s: g_b without g_W is not supported", fn);
-    rc = align_wgrad(ws.G, ws.S, ws.ones, g_W, g_b, M, Ds, Dt, P, scale, st, "dkd_wass_l1_fwdbwd: wgrad GEMM");
+    rc = align_wgrad(ws.G, ws.S, ws.ones, g_W, g_b, M, Ds, Dt, P, scale, st, "dkd_wass_l1_fwdbwd: wgrad GEMM", 1);
     if (rc != DKD_OK) return rc;
   }
   return DKD_OK;

@@ -3,8 +3,12 @@
 The generator's ReLU makes the gradient discontinuous where a pre-activation is ~0.  Two correct
 implementations with different rounding (fp32 CPU, TF32 cuDNN, bf16x3 tcgen05 ...) can gate such an element
 differently; like mask selection "given the same scores", gradient parity is defined given the same gate.
-`best_gate_oracle` evaluates the fp64 oracle with the reference gate and then greedily flips only the
-AMBIGUOUS gates (|pre-activation| < tau) while that brings the oracle gradient closer to the implementation's.
+
+Preferred form (`kernel_gate_oracle`): the kernel's OWN gate is read back (hidden activations h != 0 through
+`dkd_masked_generation_hidden_offset`), every disagreement with the fp64 oracle's gate is asserted to sit at an
+ambiguous pre-activation (|pre| < tau) and counted, and the oracle is evaluated once with that gate — nothing is
+searched or fitted.  `best_gate_oracle` (the round-1 greedy search over ambiguous gates) remains for the functional-API
+tests that do not expose the probe; it now also asserts n_flipped <= n_ambiguous.
 """
 from __future__ import annotations
 
@@ -37,7 +41,32 @@ def best_gate_oracle(eval_fn, ours: dict, tau: float = 3e-5, max_flips: int = 64
             best, best_e, flipped = (l2, g2), e2, flipped + 1
         else:
             gate[idx] = 1 - gate[idx]
+    assert flipped <= int(amb.shape[0])
     return best[0], best[1], int(amb.shape[0]), flipped
+
+
+def gate_from_hidden(hidden: torch.Tensor) -> torch.Tensor:
+    """ReLU gate [B, Dt, 14, 14] (the oracle's NCHW pre-activation layout) from the kernel's hidden planes [P, B, 196, Dt]."""
+    live = (hidden.float() != 0).any(dim=0)
+    B, N, D = live.shape
+    return live.reshape(B, 14, 14, D).permute(0, 3, 1, 2).contiguous()
+
+
+def kernel_gate_oracle(eval_fn, gate_kernel: torch.Tensor, tau: float = 3e-5):
+    """eval_fn(probe) -> (loss, grads) runs the fp64 oracle.  Evaluates it once for its own pre-activations, checks that
+    the kernel's gate differs from the oracle's only where |pre| < tau, then evaluates it with the kernel's gate.
+    Returns (loss, grads, n_ambiguous, n_differ)."""
+    probe = {}
+    eval_fn(probe)
+    pre = probe["pre"]
+    gate_kernel = gate_kernel.to(pre.device)
+    differ = gate_kernel != (pre > 0)
+    n_amb, n_diff = int((pre.abs() < tau).sum()), int(differ.sum())
+    worst = float(pre[differ].abs().max()) if n_diff else 0.0
+    assert worst < tau, f"the kernel gates an element differently at |pre| = {worst:.2e} (not ambiguous)"
+    assert n_diff <= n_amb
+    loss, grads = eval_fn({"gate": gate_kernel.to(pre.dtype)})
+    return loss, grads, n_amb, n_diff
 
 
 def case_gate_oracle(name: str, c, tau: float = 3e-5, max_flips: int = 48):

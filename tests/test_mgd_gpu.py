@@ -17,11 +17,15 @@ LOSS_RTOL = 1e-5
 GRAD_RTOL = 1e-4
 
 
-def _run(c):
+def _run(c, probe=None):
+    """One step through DistillationLoss; `probe` (dict) receives the kernel's mask and hidden activations (ReLU gate)."""
     from deltakd_b200 import DistillationLoss, call_base_loss
+    from deltakd_b200 import functional as Fn
     crit = DistillationLoss(call_base_loss(c.args), c.teacher, c.kind, c.alpha, c.tau)
     noise = c.noise
-    with mock.patch("torch.rand", side_effect=lambda *a, **k: noise.clone()):
+    real = Fn.masked_generation_loss
+    spy = (lambda *a, **k: real(*a, probe=probe, **k)) if probe is not None else real
+    with mock.patch("torch.rand", side_effect=lambda *a, **k: noise.clone()), mock.patch.object(Fn, "masked_generation_loss", spy):
         loss = crit(torch.zeros(c.B, 3, 2, 2, device="cuda"), c.outputs, c.student, c.s_feats, c.labels, c.args)
     loss.backward()
     return loss
@@ -30,14 +34,34 @@ def _run(c):
 @pytest.mark.parametrize("name", ["mgd_r05", "mgd_r03", "curkd_ep200", "vitkd"])   # vitkd = 2-layer mimic + generation (loss.py:251-311)
 def test_masked_generation_matches_reference(golden, name):
     c = build_case(name, device="cuda")
-    loss = _run(c)
+    probe = {}
+    loss = _run(c, probe)
     heads = H.head_tensors(c.student)
     for tag in ("f32", "f64"):
         ref = float(golden[f"{name}/{tag}/loss"])
         assert abs(loss.item() - ref) <= LOSS_RTOL * abs(ref), (tag, loss.item(), ref)
-    # gradients: against the fp64 oracle given the same ReLU gate (tests/gate_search.py)
-    from tests.gate_search import case_gate_oracle
-    ol, grads, ours, n_amb, n_flip = case_gate_oracle(name, c)
+    # gradients: against the fp64 oracle evaluated with the gate the KERNEL used (read back, not searched); every
+    # difference from the oracle's own gate must sit at an ambiguous pre-activation (tests/gate_search.py)
+    from tests.gate_search import gate_from_hidden, kernel_gate_oracle
+    ours = {k: p.grad.detach().double().cpu() for k, p in heads.items() if p.grad is not None}
+    for i, f in enumerate(c.s_feats):
+        if f is not None and f.grad is not None:
+            ours[f"s{i}"] = f.grad.detach().double().cpu()
+
+    def eval_fn(pr):
+        o = build_case(name, dtype=torch.float64)
+        oh = H.head_tensors(o.student)
+        l = O.distillation_loss(o.kind, o.outputs, o.labels, o.teacher_logits, o.s_feats, o.t_feats, oh, o.args,
+                                o.alpha, o.tau, noise=o.noise, probe=pr)
+        l.backward()
+        g = {k: v.grad for k, v in oh.items() if v.grad is not None}
+        for i, f in enumerate(o.s_feats):
+            if f.grad is not None:
+                g[f"s{i}"] = f.grad
+        return l, g
+
+    ol, grads, n_amb, n_flip = kernel_gate_oracle(eval_fn, gate_from_hidden(probe["hidden"]).cpu())
+    print(f"[{name}] ReLU gates: {n_amb} ambiguous, {n_flip} differ from the fp64 oracle's")
     assert abs(loss.item() - ol.item()) <= LOSS_RTOL * abs(ol.item())
     checked = 0
     for k, g in grads.items():
