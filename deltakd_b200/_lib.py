@@ -56,6 +56,8 @@ SIGNATURES = {
     "dkd_lrkd_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i, _i, _i, _i]),
     "dkd_lrkd_fwdbwd": (_i, [_i, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p,
                              _p, _sz, _p]),
+    "dkd_lrkd_eigensolve_workspace_bytes": (_sz, []),
+    "dkd_lrkd_eigensolve": (_i, [_p, _i, _i, _p, _i, _p, _sz, _p]),
     "dkd_layernorm_fwd": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "dkd_layernorm_bwd_workspace_bytes": (_sz, [_i64, _i]),
     "dkd_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),

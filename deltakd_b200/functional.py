@@ -598,6 +598,20 @@ def lrkd_layers_loss(s_feats, t_feats, linears, rank: int, coef, weight: float =
     return _LrkdLayers.apply(rank, coef, s_off, t_off, n, basis_out, *s_list, *t_list, *w_list, *b_list)
 
 
+def lrkd_eigensolve(gram: torch.Tensor, k: int = 384, algo: int = 0):
+    """Eigen-decomposition of symmetric PSD matrices [L, 384, 384] (fp64, cuda) by the LRKD eigensolver alone
+    (dkd_lrkd_eigensolve).  Returns (W, sweeps): W[l, j, :] = lambda_j v_j in an unspecified order of j (row norms =
+    eigenvalues), sweeps int32 [L].  k: leading eigenpairs wanted (the rest may be left unconverged).  The input is
+    not modified."""
+    if gram.dtype != torch.float64 or gram.dim() != 3 or gram.shape[1] != 384 or gram.shape[2] != 384 or not gram.is_cuda:
+        raise ValueError(f"lrkd_eigensolve expects a cuda fp64 tensor [L, 384, 384], got {gram.dtype} {tuple(gram.shape)}")
+    w = gram.contiguous().clone()
+    sweeps = torch.zeros(w.shape[0], dtype=torch.int32, device=w.device)
+    ws = _scratch(w.device, "lrkd_eig", _lib.lib.dkd_lrkd_eigensolve_workspace_bytes())
+    _lib.call("dkd_lrkd_eigensolve", _ptr(w), w.shape[0], int(k), _ptr(sweeps), int(algo), _ptr(ws), ws.numel(), _stream())
+    return w, sweeps
+
+
 class _FixedHead:
     def __init__(self, weight):
         self.weight, self.bias = weight, None

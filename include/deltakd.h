@@ -244,8 +244,9 @@ DKD_API int dkd_saliency_cls_score(const void* xq, int64_t xq_stride, const void
  * positive.  Vk_out[l] (fp32 [rank, Dt]) and S_out[l] (fp32 [rank], singular values) are optional outputs for
  * sign alignment and inspection; sweeps_out (int[n_layers], device) receives the Jacobi sweep counts.
  * s, t, W, bias, g_*, Vk_out, S_out are HOST arrays of n_layers device pointers (n_layers <= 8).
- * Built for Ds = 192, Dt = 384, rank <= 128.  The eigensolver is one cooperative launch (24*n_layers co-resident CTAs when that fits 148 SMs, else 12*n_layers
- * co-resident CTAs).
+ * Built for Ds = 192, Dt = 384, rank <= 128.  The eigensolver (dkd_lrkd_eigensolve below) is one launch of n_layers
+ * 16-CTA thread-block clusters; where such a cluster cannot be scheduled it falls back to one cooperative launch
+ * (24*n_layers co-resident CTAs when that fits 148 SMs, else 12*n_layers).
  */
 DKD_API size_t dkd_lrkd_workspace_bytes(int n_layers, int64_t B, int n_tok, int Ds, int Dt, int rank, int dtype,
                                         int precision);
@@ -254,6 +255,20 @@ DKD_API int dkd_lrkd_fwdbwd(int n_layers, const void* const* s, const void* cons
                             int n_tok, int Ds, int Dt, int rank, int dtype, int precision, void* const* g_s,
                             float* const* g_W, float* const* g_b, float* loss, float* const* Vk_out, float* const* S_out,
                             int* sweeps_out, void* workspace, size_t workspace_bytes, dkd_stream_t stream);
+
+/* The eigensolver of dkd_lrkd_fwdbwd on its own (tests, and the eigensolve time bench.py reports beside the roofline):
+ * W [n_layers][384][384] fp64, symmetric positive semi-definite, device memory; overwritten with the columns
+ * lambda_j v_j of its eigen-decomposition in an unspecified column order (column norms = eigenvalues).  One-sided fp64
+ * Jacobi; sweeps_out [n_layers] device ints or NULL.  k = number of leading eigenpairs the caller will read (1..384):
+ * the cluster-resident version stops when the k columns of largest norm are orthogonal to every other column (all
+ * columns are rotated in every sweep, but the trailing ones converge last and may be left unconverged); k = 384 asks
+ * for the full decomposition.  algo: 0 = what dkd_lrkd_fwdbwd uses (cluster-resident: one
+ * 16-CTA thread-block cluster per matrix, columns exchanged through distributed shared memory; falls back to the
+ * cooperative-launch version when such a cluster cannot be scheduled), 1 = cluster-resident or DKD_E_LAUNCH,
+ * 2 = cooperative launch.  Replaces the torch.linalg.svd of model/loss.py:318-324 (V of T = U S V^T). */
+DKD_API size_t dkd_lrkd_eigensolve_workspace_bytes(void);
+DKD_API int dkd_lrkd_eigensolve(double* W, int n_layers, int k, int* sweeps_out, int algo, void* workspace,
+                                size_t workspace_bytes, dkd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row operations of the token streams that feed the loss path (the callers of the path).
