@@ -14,6 +14,8 @@
 //   Loader : Params (tensor maps, extents); num_k_iters(p); issue(p, kit, m_tile, n_tile, sA, sB, bar)
 //   Epi    : Params; State; init(state); tile(p, state, m0, n0, lane_row, tmem_acc); finish(p, state)
 #pragma once
+#include <type_traits>
+
 #include "umma.cuh"
 
 namespace dkd {
@@ -54,6 +56,11 @@ struct GemmCfg {
   static_assert(TMEM_COLS_USED <= 512, "TMEM columns");
   static_assert(SMEM <= 227 * 1024, "shared memory");
 };
+
+// 16-element K steps issued per 64-wide ring stage: 4, unless the Loader says fewer (`static constexpr int K_STEPS`) — a
+// per-head attention operand is 48 channels wide: the 64-wide box is loaded, the MMAs stop after 3 steps.
+template <class L, class = void> struct loader_ksteps { static constexpr int value = 4; };
+template <class L> struct loader_ksteps<L, std::void_t<decltype(L::K_STEPS)>> { static constexpr int value = L::K_STEPS; };
 
 template <class Loader, class Epi>
 struct GemmParams {
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_tn_kernel(const __grid_c
               const uint32_t a_pl = a_addr + (Cfg::PLANES == 2 && term == 1 ? Cfg::A_BYTES : 0);
               const uint32_t b_pl = b_addr + (Cfg::PLANES == 2 && term == 0 ? Cfg::B_BYTES : 0);
 #pragma unroll
-              for (int k = 0; k < Cfg::BK / 16; ++k) {
+              for (int k = 0; k < loader_ksteps<Loader>::value; ++k) {
                 const uint64_t da = kmajor_desc(a_pl + k * 32);
 #pragma unroll
                 for (int ni = 0; ni < Cfg::NI; ++ni) {

@@ -92,6 +92,12 @@ __global__ void __launch_bounds__(192) teacher_planes_kernel(const T* __restrict
     sumsq_part[(size_t)blockIdx.x * kN + c] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
 }
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---------------------------------------------------------------- 2. Gram: per-split partial tiles -> fp64, symmetric
 using GramCfg = GemmNtCfg<6, false, 256, 128, 3, 64>;   // 128 x 384 fp32 tile in TMEM, 64 rows per stage
 
@@ -116,19 +122,22 @@ __global__ void gram_reduce_kernel(const float* __restrict__ part, int splits, d
   gsum[idx] = a;
 }
 
-__global__ void gram_symmetrize_kernel(const double* __restrict__ gsum, const double* __restrict__ sumsq_part, int nparts,
-                                       double* __restrict__ W) {
+// off-diagonal: 0.5 (g_ij + g_ji); diagonal: the exact fp64 column sums of squares, folded over the partial blocks by
+// one warp per column in a fixed order (a thread-per-column loop over 296 partials was a 26 us chain of L2 round trips)
+__global__ void __launch_bounds__(256) gram_symmetrize_kernel(const double* __restrict__ gsum, const double* __restrict__ sumsq_part,
+                                                              int nparts, double* __restrict__ W) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= kN * kN) return;
-  const int i = idx / kN, j = idx - i * kN;
-  double v;
-  if (i == j) {
-    v = 0.0;
-    for (int s = 0; s < nparts; ++s) v += sumsq_part[(size_t)s * kN + i];
-  } else {
-    v = 0.5 * (gsum[idx] + gsum[j * kN + i]);
+  if (idx < kN * kN) {
+    const int i = idx / kN, j = idx - i * kN;
+    if (i != j) W[idx] = 0.5 * (gsum[idx] + gsum[j * kN + i]);
   }
-  W[idx] = v;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp_global < kN) {
+    double v = 0.0;
+    for (int s = lane; s < nparts; s += 32) v += sumsq_part[(size_t)s * kN + warp_global];
+    v = warp_sum_d(v);
+    if (lane == 0) W[(size_t)warp_global * kN + warp_global] = v;
+  }
 }
 
 // ---------------------------------------------------------------- 3. batched one-sided Jacobi (cooperative launch)
@@ -161,12 +170,6 @@ __device__ __forceinline__ void layer_barrier(unsigned* ctr, unsigned target) {
     __threadfence();
   }
   __syncthreads();
-}
-
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
 }
 
 // Two-level (block) one-sided Jacobi.  The 384 columns form 24 groups of 16; in an outer round every CTA owns a pair

@@ -4,9 +4,9 @@
 //
 //   method 1 (misc.py:62-70, models.py:46-56): self-attention over the patch tokens, 8 heads x 48;
 //       score_i = mean_h softmax_j(q_i . k_j * 48^-1/2)[i]  — only the DIAGONAL of each head's map is used,
-//       so the maps are never materialised: the qk projection runs on tcgen05 (gemm_tn, fp32 rows to scratch)
-//       and one CTA per sample walks the heads with K_h in shared memory, one query row per thread, online
-//       softmax in registers.
+//       so the maps are never materialised: the qk projection runs on tcgen05 and writes q, k as bf16 planes; a second
+//       tcgen05 GEMM per (sample, head, query half) leaves the 128 x 196 logits in tensor memory, where the epilogue
+//       reduces every row to its softmax diagonal (online softmax in registers, MUFU ex2).
 //   method 2 (misc.py:88-116): query = CLS token only, keys = [CLS] + patches; score = head-mean of that row,
 //       patches only.      method 3 (misc.py:135-148, models.py:24-35): CLS -> patches cross attention.
 //       With one query per sample the key projection is folded into the query:
@@ -117,12 +117,17 @@ __global__ void __launch_bounds__(256) cls_score_kernel(ClsParams p) {
 }
 
 // ---------------------------------------------------------------- method 1: diagonal of the self-attention maps
-struct DiagParams {
-  const float* qk;   // [B*n_tok, 2*D] fp32: q = cols [0, D), k = cols [D, 2D)
-  float* score;      // [B, n_tok]
-  int n_tok, D, H;
-  float scale;
-};
+// Two tcgen05 GEMMs, no map materialised:
+//   1. qk = X W^T + b, written by the epilogue as THREE bf16 planes (hi, mid, lo = all 24 mantissa bits) of [M, 2D];
+//      the q half carries 48^-1/2 log2(e), so the logits below are in base 2
+//   2. per (sample, head): S = q_h k_h^T on the tensor core — M tile 128 query rows, N = 208 key rows, K = 48: the
+//      64-channel box that starts at the head's first channel is loaded and the MMAs stop after 3 K steps; six plane
+//      products (fp32-exact operands: the scores rank tokens, a 1e-5 logit error flips masks).  The epilogue keeps the
+//      accumulator row in registers chunk by chunk: online softmax over the 196 real keys and the diagonal entry,
+//      p_ii = 2^(s_ii - m) / l, stored per head; a last small kernel averages the heads in a fixed order.
+// The SIMT version of step 2 (one CTA per sample, K_h in shared memory, one query row per thread) took 954 us of the
+// 5.85 ms saliency-MGD call at B = 512: 15 GFLOP of fp32 FMAs fed from shared memory.
+constexpr int kQkPlanes = 3;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -130,80 +135,141 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(256) selfdiag_score_kernel(DiagParams p) {
-  extern __shared__ float sm[];
-  float* ks = sm;  // [n_tok][48]
-  const int b = blockIdx.x, i = threadIdx.x;
-  const int ld = 2 * p.D;
-  const float* base = p.qk + (size_t)b * p.n_tok * ld;
-  const bool live = i < p.n_tok;
-  float total = 0.f;
-  for (int h = 0; h < p.H; ++h) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < p.n_tok * (kHeadDim / 4); idx += blockDim.x) {
-      const int j = idx / (kHeadDim / 4), c = (idx - j * (kHeadDim / 4)) * 4;
-      *reinterpret_cast<float4*>(ks + j * kHeadDim + c) =
-          *reinterpret_cast<const float4*>(base + (size_t)j * ld + p.D + h * kHeadDim + c);
-    }
-    __syncthreads();
-    if (!live) continue;
-    float q[kHeadDim];
-#pragma unroll
-    for (int c = 0; c < kHeadDim; c += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)i * ld + h * kHeadDim + c);
-      const float sc = p.scale * 1.4426950408889634f;   // logits in base 2
-      q[c] = v.x * sc; q[c + 1] = v.y * sc; q[c + 2] = v.z * sc; q[c + 3] = v.w * sc;
-    }
-    // online softmax in base 2 over groups of 4 keys: one rescale per group (branch-free), MUFU ex2 (relative error 2^-22,
-    // far inside the 1e-5 score gate); the logits carry log2(e) through the pre-scaled query
-    float m = -INFINITY, l = 0.f, sii = 0.f;
-    auto dot = [&](int j) {
-      const float4* kr = reinterpret_cast<const float4*>(ks + j * kHeadDim);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < kHeadDim / 4; ++c) {
-        const float4 kv = kr[c];
-        a0 = fmaf(q[4 * c], kv.x, a0); a1 = fmaf(q[4 * c + 1], kv.y, a1);
-        a2 = fmaf(q[4 * c + 2], kv.z, a2); a3 = fmaf(q[4 * c + 3], kv.w, a3);
-      }
-      return (a0 + a1) + (a2 + a3);
-    };
-    int j = 0;
-    for (; j + 4 <= p.n_tok; j += 4) {
-      const float s0 = dot(j), s1 = dot(j + 1), s2 = dot(j + 2), s3 = dot(j + 3);
-      sii = i == j ? s0 : i == j + 1 ? s1 : i == j + 2 ? s2 : i == j + 3 ? s3 : sii;
-      const float mn = fmaxf(fmaxf(m, fmaxf(s0, s1)), fmaxf(s2, s3));
-      l = l * ex2(m - mn) + ((ex2(s0 - mn) + ex2(s1 - mn)) + (ex2(s2 - mn) + ex2(s3 - mn)));
-      m = mn;
-    }
-    for (; j < p.n_tok; ++j) {
-      const float s0 = dot(j);
-      sii = i == j ? s0 : sii;
-      const float mn = fmaxf(m, s0);
-      l = l * ex2(m - mn) + ex2(s0 - mn);
-      m = mn;
-    }
-    total += ex2(sii - m) / l;
-  }
-  if (live) p.score[(size_t)b * p.n_tok + i] = total / (float)p.H;
-}
-
 using QkCfg = GemmCfg<192, 1, 4, 2>;
+
+struct QkPlanesParams {
+  __nv_bfloat16* planes;   // [3][M][2D]
+  const float* bias;       // [2D] or null
+  int64_t M;
+  int D;
+  float qscale;            // applied to the q half (columns < D)
+};
+struct QkPlanesEpi {
+  using Params = QkPlanesParams;
+  struct State {};
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int n0, int row_in_tile, uint32_t t_acc) {
+    const int64_t m = (int64_t)m0 + row_in_tile;
+    const bool live = m < p.M;
+    const float sc = n0 < p.D ? p.qscale : 1.f;      // BN = 192 divides D = 384: a tile is all q or all k
+    const int64_t plane = p.M * 2 * p.D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < QkCfg::BN; c0 += 32) {
+      float v[32];
+      sm100::tmem_ld32(t_acc + c0, v);
+      sm100::tmem_ld_wait();
+      if (!live) continue;
+      float bs[32];
+      ldg_vec32(p.bias ? p.bias + n0 + c0 : nullptr, bs);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (v[j] + bs[j]) * sc;
+      __nv_bfloat16* op = p.planes + m * 2 * p.D + n0 + c0;
+#pragma unroll
+      for (int pl = 0; pl < kQkPlanes; ++pl) {
+        stg256(op + pl * plane, *reinterpret_cast<float(*)[16]>(&v[0]));
+        stg256(op + pl * plane + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
+        if (pl + 1 < kQkPlanes) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+};
+
+// tile index mt = ((b * H + h) * 2 + half): query rows [128 half, 128 half + 128) of sample b, head h; one N tile
+using ScoreCfg = GemmCfg<208, 1, 4, 2>;
+struct ScoreLoaderParams {
+  CUtensorMap tmQ, tmK;   // 4-D {2D, n_tok, B, planes}; Q: box {64, 128, 1, 1}, K: box {64, 208, 1, 1}
+  int H, D;
+};
+struct ScoreLoader {
+  using Params = ScoreLoaderParams;
+  static constexpr int K_STEPS = kHeadDim / 16;   // 3 of the 4 K steps of a 64-channel stage
+  static constexpr uint32_t TX_BYTES = ScoreCfg::STAGE_BYTES;
+  static __device__ __forceinline__ int num_k_iters(const Params&) { return 6; }
+  static __device__ __forceinline__ void prefetch(const Params& p) { sm100::tma_prefetch_desc(&p.tmQ); sm100::tma_prefetch_desc(&p.tmK); }
+  static __device__ __forceinline__ void issue(const Params& p, int kit, int mt, int, uint8_t* sA, uint8_t* sB, uint64_t* bar) {
+    int pa, pb;
+    term_planes(kit, 6, pa, pb);
+    const int half = mt & 1, bh = mt >> 1, h = bh % p.H, b = bh / p.H;
+    sm100::tma_load_4d(sA, &p.tmQ, bar, h * kHeadDim, half * 128, b, pa);
+    sm100::tma_load_4d(sB, &p.tmK, bar, p.D + h * kHeadDim, 0, b, pb);
+  }
+};
+struct DiagEpiParams {
+  float* head_score;   // [B][H][n_tok]
+  int n_tok, H;
+};
+struct DiagEpi {
+  using Params = DiagEpiParams;
+  struct State {};
+  static __device__ __forceinline__ void init(const Params&, State&) {}
+  static __device__ __forceinline__ void tile(const Params& p, State&, int m0, int, int row_in_tile, uint32_t t_acc) {
+    const int mt = m0 >> 7;
+    const int half = mt & 1, bh = mt >> 1;
+    const int i = half * 128 + row_in_tile;         // query token
+    float m = -INFINITY, l = 0.f, sii = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 192; c0 += 32) {
+      float v[32];
+      sm100::tmem_ld32(t_acc + c0, v);
+      sm100::tmem_ld_wait();
+      float c[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+      for (int j = 4; j < 32; j += 4) { c[0] = fmaxf(c[0], v[j]); c[1] = fmaxf(c[1], v[j + 1]); c[2] = fmaxf(c[2], v[j + 2]); c[3] = fmaxf(c[3], v[j + 3]); }
+      const float mn = fmaxf(m, fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3])));
+      float s0 = l * ex2(m - mn), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        s0 += ex2(v[j] - mn); s1 += ex2(v[j + 1] - mn); s2 += ex2(v[j + 2] - mn); s3 += ex2(v[j + 3] - mn);
+      }
+      l = (s0 + s1) + (s2 + s3); m = mn;
+      if ((i >> 5) == (c0 >> 5)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sii = (i & 31) == j ? v[j] : sii;
+      }
+    }
+    {
+      float v[32];
+      sm100::tmem_ld32(t_acc + 176, v);   // columns 176..207: keys 192..195 are v[16..19]
+      sm100::tmem_ld_wait();
+      const float mn = fmaxf(m, fmaxf(fmaxf(v[16], v[17]), fmaxf(v[18], v[19])));
+      l = l * ex2(m - mn) + ((ex2(v[16] - mn) + ex2(v[17] - mn)) + (ex2(v[18] - mn) + ex2(v[19] - mn)));
+      m = mn;
+      if (i >= 192) sii = i == 192 ? v[16] : i == 193 ? v[17] : i == 194 ? v[18] : v[19];
+    }
+    if (i < p.n_tok) p.head_score[(size_t)bh * p.n_tok + i] = ex2(sii - m) / l;
+  }
+  static __device__ __forceinline__ void finish(const Params&, State&, int) {}
+};
+
+__global__ void __launch_bounds__(256) head_mean_kernel(const float* __restrict__ hs, float* __restrict__ score, int64_t total, int n_tok, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t b = idx / n_tok, i = idx - b * n_tok;
+  float t = 0.f;
+  for (int h = 0; h < H; ++h) t += hs[((size_t)b * H + h) * n_tok + i];
+  score[idx] = t / (float)H;
+}
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Workspace {
-  __nv_bfloat16 *X, *Wp;
-  float* QK;
+  __nv_bfloat16 *X, *Wp, *QK;
+  float* HS;
   size_t bytes;
 };
-Workspace carve(void* base, int64_t M, int D, int P) {
+Workspace carve(void* base, int64_t B, int n_tok, int D, int P, int H) {
   Workspace w;
+  const int64_t M = B * n_tok;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 1024); return reinterpret_cast<char*>(base) + o; };
   w.X = reinterpret_cast<__nv_bfloat16*>(take((size_t)P * M * D * 2));
   w.Wp = reinterpret_cast<__nv_bfloat16*>(take((size_t)P * 2 * D * D * 2));
-  w.QK = reinterpret_cast<float*>(take((size_t)M * 2 * D * 4));
+  w.QK = reinterpret_cast<__nv_bfloat16*>(take((size_t)kQkPlanes * M * 2 * D * 2));
+  w.HS = reinterpret_cast<float*>(take((size_t)B * H * n_tok * 4));
   w.bytes = off;
   return w;
 }
@@ -243,7 +309,7 @@ int dkd_saliency_cls_score(const void* xq, int64_t xq_stride, const void* xk, in
 }
 
 size_t dkd_saliency_selfdiag_workspace_bytes(int64_t B, int n_tok, int D, int precision) {
-  return dkd::carve(nullptr, B * n_tok, D, precision == DKD_PREC_BF16X3 ? 2 : 1).bytes;
+  return dkd::carve(nullptr, B, n_tok, D, precision == DKD_PREC_BF16X3 ? 2 : 1, 8).bytes;
 }
 
 int dkd_saliency_selfdiag_score(const void* x, int64_t B, int T, int off, int n_tok, int D, int dtype, const float* qk_w,
@@ -255,8 +321,8 @@ int dkd_saliency_selfdiag_score(const void* x, int64_t B, int T, int off, int n_
   const char* fn = "dkd_saliency_selfdiag_score";
   DKD_REQUIRE(dtype == DKD_F32 || dtype == DKD_BF16, DKD_E_DTYPE, "%s: dtype %d", fn, dtype);
   DKD_REQUIRE(precision == DKD_PREC_BF16 || precision == DKD_PREC_BF16X3, DKD_E_UNSUPPORTED, "%s: precision %d", fn, precision);
-  DKD_REQUIRE(B >= 0 && n_tok > 0 && n_tok <= kMaxKeys && off >= 0 && T >= off + n_tok, DKD_E_SHAPE, "%s: bad token geometry (n_tok <= %d)", fn,
-              kMaxKeys);
+  DKD_REQUIRE(B >= 0 && n_tok == 196 && off >= 0 && T >= off + n_tok, DKD_E_SHAPE,
+              "%s: built for 196 patch tokens per sample (two 128-row query tiles, 208-column key tile), got %d", fn, n_tok);
   DKD_REQUIRE(num_heads == 8 && D == num_heads * kHeadDim, DKD_E_SHAPE, "%s: built for 8 heads x 48 (D = 384), got %d heads, D = %d", fn,
               num_heads, D);
   if (B == 0) return DKD_OK;
@@ -265,7 +331,8 @@ int dkd_saliency_selfdiag_score(const void* x, int64_t B, int T, int off, int n_
   const int P = precision == DKD_PREC_BF16X3 ? 2 : 1;
   const int64_t M = B * n_tok;
   DKD_REQUIRE(M < (1ll << 31) - 256, DKD_E_SHAPE, "%s: too many rows", fn);
-  Workspace ws = carve(workspace, M, D, P);
+  DKD_REQUIRE(B * num_heads * 2 < (1ll << 31), DKD_E_SHAPE, "%s: too many (sample, head) tiles", fn);
+  Workspace ws = carve(workspace, B, n_tok, D, P, num_heads);
   DKD_REQUIRE(workspace_bytes >= ws.bytes, DKD_E_WORKSPACE, "%s: workspace %zu < %zu", fn, workspace_bytes, ws.bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -273,18 +340,18 @@ int dkd_saliency_selfdiag_score(const void* x, int64_t B, int T, int off, int n_
   if (rc != DKD_OK) return rc;
   rc = launch_weight_to_planes(qk_w, 2 * D, D, P, ws.Wp, nullptr, st);
   if (rc != DKD_OK) return rc;
-  {  // qk = X W^T + b  (fp32 rows)
+  {  // qk = X W^T + b  as three bf16 planes, q pre-scaled
     using Cfg = QkCfg;
     using L = PlaneLoader<Cfg>;
-    using E = StoreRowsEpi<Cfg>;
+    using E = QkPlanesEpi;
     GemmParams<L, E> p;
     rc = make_plane_tmap(&p.ld.tmA, ws.X, P, M, D, D, M * D, Cfg::BM, "saliency X");
     if (rc != DKD_OK) return rc;
     rc = make_plane_tmap(&p.ld.tmB, ws.Wp, P, 2 * D, D, D, (int64_t)2 * D * D, Cfg::BN, "saliency qk weight");
     if (rc != DKD_OK) return rc;
     p.ld.k_blocks = D / 64; p.ld.nterms = P == 2 ? 3 : 1;
-    p.ep.out = ws.QK; p.ep.drop_mask = nullptr; p.ep.bias = qk_b; p.ep.alpha = 1.f;
-    p.ep.M = M; p.ep.N_total = 2 * D; p.ep.n_tok = (int)M; p.ep.T_out = (int)M; p.ep.off = 0; p.ep.out_is_bf16 = 0;
+    p.ep.planes = ws.QK; p.ep.bias = qk_b; p.ep.M = M; p.ep.D = D;
+    p.ep.qscale = 1.4426950408889634f / sqrtf((float)kHeadDim);
     p.m_tiles = (int)((M + Cfg::BM - 1) / Cfg::BM); p.n_tiles = 2 * D / Cfg::BN;
     const int grid = min(kNumSMs, p.m_tiles * p.n_tiles);
     auto kern = gemm_tn_kernel<Cfg, L, E>;
@@ -293,12 +360,27 @@ int dkd_saliency_selfdiag_score(const void* x, int64_t B, int T, int off, int n_
     rc = check_launch("dkd_saliency_selfdiag_score: qk GEMM");
     if (rc != DKD_OK) return rc;
   }
-  DiagParams dp;
-  dp.qk = ws.QK; dp.score = score; dp.n_tok = n_tok; dp.D = D; dp.H = num_heads; dp.scale = 1.0f / sqrtf((float)kHeadDim);
-  const size_t smem = (size_t)n_tok * kHeadDim * sizeof(float);
-  const int threads = (n_tok + 31) / 32 * 32;
-  cudaFuncSetAttribute(selfdiag_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  selfdiag_score_kernel<<<(unsigned)B, threads, smem, st>>>(dp);
+  {  // per (sample, head): softmax diagonal of q_h k_h^T
+    using Cfg = ScoreCfg;
+    GemmParams<ScoreLoader, DiagEpi> p;
+    const uint64_t dims[4] = {(uint64_t)(2 * D), (uint64_t)n_tok, (uint64_t)B, (uint64_t)kQkPlanes};
+    const uint64_t strides[3] = {(uint64_t)2 * D * 2, (uint64_t)n_tok * 2 * D * 2, (uint64_t)M * 2 * D * 2};
+    const uint32_t box_q[4] = {64, 128, 1, 1}, box_k[4] = {64, 208, 1, 1};
+    rc = make_tmap_bf16(&p.ld.tmQ, ws.QK, 4, dims, strides, box_q, "saliency q planes");
+    if (rc != DKD_OK) return rc;
+    rc = make_tmap_bf16(&p.ld.tmK, ws.QK, 4, dims, strides, box_k, "saliency k planes");
+    if (rc != DKD_OK) return rc;
+    p.ld.H = num_heads; p.ld.D = D;
+    p.ep.head_score = ws.HS; p.ep.n_tok = n_tok; p.ep.H = num_heads;
+    p.m_tiles = (int)(B * num_heads * 2); p.n_tiles = 1;
+    const int grid = min(kNumSMs, p.m_tiles);
+    auto kern = gemm_tn_kernel<Cfg, ScoreLoader, DiagEpi>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+    rc = check_launch("dkd_saliency_selfdiag_score: score GEMM");
+    if (rc != DKD_OK) return rc;
+  }
+  head_mean_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(ws.HS, score, M, n_tok, num_heads);
   return check_launch(fn);
 }
 

@@ -25,10 +25,13 @@ namespace {
 
 constexpr int kTok = 196;                   // points per cloud (14 x 14 patch tokens)
 constexpr int kD = 384;                     // teacher width
-constexpr int kLD = 204;                    // allocation pitch of a cost matrix in floats (and the pitch of C_xy)
-constexpr int kLDxy = 204;                  // C_xy: one thread per row -> 8 consecutive rows hit 8 distinct 16-byte bank groups
-constexpr int kLDsym = 196;                 // C_xx, C_yy: two threads per row (float4 chunks [0,28) | [28,49)): 4i + 16h distinct bank groups
-constexpr int kCostBytes = kTok * kLD * 4;  // 159 936 (copied whole; the symmetric matrices use the first 196*200 floats)
+constexpr int kLD = 200;                    // pitch of a cost matrix in floats, global and shared: with four threads per row (LDS.128,
+                                            // float4 chunks [0,12) [12,25) [25,37) [37,49)) the 2 rows x 4 parts of a quarter warp hit the 8
+                                            // distinct 16-byte bank groups (50 = 2 mod 8; part offsets 0, 4, 1, 5), and with four threads
+                                            // per column (LDS.32, rows = part mod 4) a warp hits 32 distinct banks (200 = 8 mod 32)
+constexpr int kLDxy = kLD;
+constexpr int kLDsym = kLD;
+constexpr int kCostBytes = kTok * kLD * 4;  // 156 800 (one bulk copy)
 constexpr int kLDP = 208;                   // plan row pitch in bf16 (416 B)
 constexpr int kMaxEps = 64;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -201,56 +204,83 @@ __device__ __forceinline__ void load_cost(float* sC, const float* gC, uint64_t* 
   mbar_wait(bar, 0);
 }
 
-// One-pass ("online") base-2 log-sum-exp.  Values v_j = h[j] - C[.][j]*c2 are produced in chunks of up to 28; the
-// running maximum m and the sum s = sum 2^(v - m) are rescaled when a chunk raises the maximum (one extra ex2 per
-// chunk) — each cost entry is read from shared memory once per eps step instead of twice.
+// One-pass ("online") base-2 log-sum-exp.  Values v_j = h[j] - C[.][j]*c2 are produced in chunks of NV; the running
+// maximum m and the sum s = sum 2^(v - m) are rescaled when a chunk raises the maximum (one extra ex2 per chunk) —
+// each cost entry is read from shared memory once per eps step instead of twice.
 struct Lse { float m, s; };
-__device__ __forceinline__ void lse_push(Lse& a, const float (&v)[28]) {
-  float c0 = fmaxf(v[0], v[1]), c1 = fmaxf(v[2], v[3]), c2 = fmaxf(v[4], v[5]), c3 = fmaxf(v[6], v[7]);
+template <int NV>
+__device__ __forceinline__ void lse_push(Lse& a, const float (&v)[NV]) {
+  static_assert(NV % 4 == 0, "chunks of whole float4");
+  float c0 = v[0], c1 = v[1], c2 = v[2], c3 = v[3];
 #pragma unroll
-  for (int q = 8; q < 28; q += 4) { c0 = fmaxf(c0, v[q]); c1 = fmaxf(c1, v[q + 1]); c2 = fmaxf(c2, v[q + 2]); c3 = fmaxf(c3, v[q + 3]); }
+  for (int q = 4; q < NV; q += 4) { c0 = fmaxf(c0, v[q]); c1 = fmaxf(c1, v[q + 1]); c2 = fmaxf(c2, v[q + 2]); c3 = fmaxf(c3, v[q + 3]); }
   const float mn = fmaxf(a.m, fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
   float s0 = a.s * ex2f(a.m - mn), s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int q = 0; q < 28; q += 4) {
+  for (int q = 0; q < NV; q += 4) {
     s0 += ex2f(v[q + 0] - mn); s1 += ex2f(v[q + 1] - mn);
     s2 += ex2f(v[q + 2] - mn); s3 += ex2f(v[q + 3] - mn);
   }
   a.m = mn; a.s = (s0 + s1) + (s2 + s3);
 }
-// float4 chunks [k0, k1) of one row; k1 - k0 is a multiple of 7 (a row is 49 = 7 x 7 chunks)
+__device__ __forceinline__ Lse lse_merge(const Lse& a, const Lse& b) {
+  const float m = fmaxf(a.m, b.m);
+  return Lse{m, a.s * ex2f(a.m - m) + b.s * ex2f(b.m - m)};
+}
+// the four lanes 4i .. 4i+3 hold the parts of one row (or column): everybody gets the whole
+__device__ __forceinline__ Lse lse_merge4(Lse a) {
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    Lse b;
+    b.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+    b.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+    a = lse_merge(a, b);
+  }
+  return a;
+}
+// float4 chunks [k0, k1) of one row: groups of four chunks, then single chunks
 __device__ __forceinline__ Lse lse2_row_part(const float* __restrict__ crow, const float* __restrict__ h, float c2, int k0, int k1) {
   const float4* c4 = reinterpret_cast<const float4*>(crow);
   const float4* h4 = reinterpret_cast<const float4*>(h);
   Lse a{-INFINITY, 0.f};
+  int kb = k0;
 #pragma unroll 1
-  for (int kb = k0; kb < k1; kb += 7) {
-    float v[28];
+  for (; kb + 4 <= k1; kb += 4) {
+    float v[16];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) {
+    for (int q = 0; q < 4; ++q) {
       const float4 c = c4[kb + q], hh = h4[kb + q];
       v[4 * q] = fmaf(-c.x, c2, hh.x); v[4 * q + 1] = fmaf(-c.y, c2, hh.y);
       v[4 * q + 2] = fmaf(-c.z, c2, hh.z); v[4 * q + 3] = fmaf(-c.w, c2, hh.w);
     }
     lse_push(a, v);
   }
-  return a;
-}
-// whole column j of C_xy (stride kLDxy; consecutive threads -> consecutive banks)
-__device__ __forceinline__ Lse lse2_col(const float* __restrict__ ccol, const float* __restrict__ h, float c2) {
-  Lse a{-INFINITY, 0.f};
 #pragma unroll 1
-  for (int i0 = 0; i0 < kTok; i0 += 28) {
-    float v[28];
-#pragma unroll
-    for (int q = 0; q < 28; ++q) v[q] = fmaf(-ccol[(i0 + q) * kLDxy], c2, h[i0 + q]);
+  for (; kb < k1; ++kb) {
+    const float4 c = c4[kb], hh = h4[kb];
+    const float v[4] = {fmaf(-c.x, c2, hh.x), fmaf(-c.y, c2, hh.y), fmaf(-c.z, c2, hh.z), fmaf(-c.w, c2, hh.w)};
     lse_push(a, v);
   }
   return a;
 }
-__device__ __forceinline__ Lse lse_merge(const Lse& a, const Lse& b) {
-  const float m = fmaxf(a.m, b.m);
-  return Lse{m, a.s * ex2f(a.m - m) + b.s * ex2f(b.m - m)};
+// rows part, part + 4, part + 8, ... (49 of them) of column j of C_xy; hp = this part's slice of the part-major h vector
+__device__ __forceinline__ Lse lse2_col_part(const float* __restrict__ ccol, const float* __restrict__ hp, float c2) {
+  const float4* h4 = reinterpret_cast<const float4*>(hp);
+  Lse a{-INFINITY, 0.f};
+#pragma unroll 1
+  for (int q0 = 0; q0 < 48; q0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 hh = h4[(q0 >> 2) + q];
+      const float* c = ccol + (size_t)(q0 + 4 * q) * 4 * kLDxy;
+      v[4 * q] = fmaf(-c[0], c2, hh.x); v[4 * q + 1] = fmaf(-c[4 * kLDxy], c2, hh.y);
+      v[4 * q + 2] = fmaf(-c[8 * kLDxy], c2, hh.z); v[4 * q + 3] = fmaf(-c[12 * kLDxy], c2, hh.w);
+    }
+    lse_push(a, v);
+  }
+  const float last = fmaf(-ccol[(size_t)48 * 4 * kLDxy], c2, hp[48]);
+  return lse_merge(a, Lse{last, 1.f});
 }
 
 // plan row segment:  sign * 2^(h[j] - C[i][j]*c2 - m) / s  as bf16 hi / lo, float4 chunks [k0, k1), 8-byte stores
@@ -259,7 +289,7 @@ __device__ __forceinline__ void write_plan_part(const float* __restrict__ crow, 
   const float4* c4 = reinterpret_cast<const float4*>(crow);
   const float4* h4 = reinterpret_cast<const float4*>(h);
   const float inv = sign / s;
-#pragma unroll 5
+#pragma unroll 4
   for (int k = k0; k < k1; ++k) {
     const float4 c = c4[k], hh = h4[k];
     float v[4], r[4];
@@ -272,72 +302,74 @@ __device__ __forceinline__ void write_plan_part(const float* __restrict__ crow, 
   }
 }
 
-constexpr int kRoleThreads = 224;   // xy kernel: 7 warps per role (rows | columns), 196 threads of each active
-constexpr int kSymThreads = 416;    // symmetric kernel: two threads per row (392 active)
-constexpr size_t kSinkSmem = (size_t)kCostBytes + 4 * kTok * sizeof(float) + 64;
+constexpr int kSinkThreads = 800;   // 25 warps: four threads per row — and, for C_xy, the same four per column
+constexpr int kHP = 52;             // part-major h vector: [4][52] (49 used)
+constexpr size_t kSinkSmem = (size_t)kCostBytes + (2 * kTok + 2 * 4 * kHP + kMaxEps) * sizeof(float) + 64;
 
 // Step schedule (geomloss sinkhorn_loop): step -1 initialises the potentials at eps[0] from the log-weights alone,
 // steps 0..n-1 average (symmetric update) at eps[k], step n is the final extrapolation at eps[n-1] (plain assignment).
-//   XY  : one CTA per pair, cost C_xy; thread i < 196 of role 0 owns row i (f_ba), thread j of role 1 column j (g_ab)
-//   !XY : one CTA per (pair, xx | yy); threads 2i, 2i+1 own the two halves of row i (f_aa or g_bb)
+//   XY  : one CTA per pair, cost C_xy; lanes 4i .. 4i+3 own row i (f_ba[i], a quarter of the row each) AND column i
+//         (g_ab[i], rows = lane mod 4): every thread does the same work, 98 cost entries per eps step
+//   !XY : one CTA per (pair, xx | yy); lanes 4i .. 4i+3 own row i (f_aa or g_bb)
+// ncu of the previous layout (one thread per row / column, 14 warps, the 7th warp of each role nearly empty): XU pipe
+// 54 % busy, top stalls MIO throttle (MUFU and LDS share the queue; the column threads issued 2 LDS per entry), wait,
+// barrier (row warps waiting for the slower column warps) and long scoreboard (eps read from global memory each step).
 template <bool XY>
-__global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kSymThreads, 1) sinkhorn_kernel(SinkParams p) {
+__global__ void __launch_bounds__(kSinkThreads, 1) sinkhorn_kernel(SinkParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   float* sC = reinterpret_cast<float*>(smem_raw);
-  float* hR = sC + kTok * kLD;            // [2][196] : h over columns j, read by the row threads
-  float* hC = hR + 2 * kTok;              // [2][196] : h over rows i, read by the column threads (xy only)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(hC + 2 * kTok);
-  __shared__ double red[16];
-  constexpr int LD = XY ? kLDxy : kLDsym;
-  constexpr int K4 = kTok / 4;            // 49 float4 chunks per row
+  float* hR = sC + kTok * kLD;            // [2][196]     : h over columns j (from g_ab; xx, yy: from the potential itself), read by the row work
+  float* hC = hR + 2 * kTok;              // [2][4][kHP]  : h over rows i (from f_ba), part-major: entry i at [i & 3][i >> 2]; read by the column work
+  float* s_eps = hC + 2 * 4 * kHP;        // [kMaxEps]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_eps + kMaxEps);
+  __shared__ double red[32];
+  constexpr int LD = kLD;
 
   const int pair = XY ? blockIdx.x : blockIdx.x >> 1;
   const int which = XY ? 0 : 1 + (blockIdx.x & 1);
-  load_cost(sC, p.C + (size_t)(pair * 3 + which) * kTok * kLD, bar);
-
   const int n = p.n_eps[pair];
-  const float* eps_list = p.eps + (size_t)pair * kMaxEps;
-  const bool is_col = XY && threadIdx.x >= kRoleThreads;
-  const int idx = XY ? (is_col ? threadIdx.x - kRoleThreads : threadIdx.x) : threadIdx.x >> 1;   // row i or column j
-  const int half = XY ? 0 : threadIdx.x & 1;
-  const int k0 = XY ? 0 : (half ? 28 : 0), k1 = XY ? K4 : (half ? K4 : 28);   // this thread's float4 chunks of its row (4 | 3 groups of 7)
+  if ((int)threadIdx.x < kMaxEps) s_eps[threadIdx.x] = p.eps[(size_t)pair * kMaxEps + threadIdx.x];
+  if ((int)threadIdx.x < 2 * 4 * kHP) hC[threadIdx.x] = 0.f;
+  load_cost(sC, p.C + (size_t)(pair * 3 + which) * kTok * kLD, bar);   // (contains the __syncthreads that publishes s_eps)
+
+  const int idx = threadIdx.x >> 2, part = threadIdx.x & 3;   // row (and column) idx, quarter `part`
+  const int k0 = part == 0 ? 0 : (part == 1 ? 12 : (part == 2 ? 25 : 37));
+  const int k1 = part == 0 ? 12 : (part == 1 ? 25 : (part == 2 ? 37 : 49));
   const bool active = idx < kTok;
+  const int row = active ? idx : 0;       // idle lanes of the last warp walk row 0 (results unused)
   const float logw = -__logf((float)kTok);
-  float pot = 0.f;            // f_ba[i] / g_ab[j] (xy) or f_aa[i] / g_bb[i] (sym; both halves hold the same value)
+  float pot_f = 0.f, pot_g = 0.f;         // f_ba[idx] and (xy) g_ab[idx]; xx / yy: the one potential in pot_f
   Lse fin{0.f, 1.f};
   float c2_fin = 0.f;
 
   for (int step = -1; step <= n; ++step) {
-    const float eps = eps_list[step < 0 ? 0 : (step < n ? step : n - 1)];
+    const float eps = s_eps[step < 0 ? 0 : (step < n ? step : n - 1)];
+    const float inv_eps = 1.f / eps;
     const int buf = (step + 1) & 1;
-    // this thread's potential becomes an entry of the h vector the OTHER role reads (same role for the symmetric problems)
-    if (active && half == 0) {
-      const float hv = (logw + (step < 0 ? 0.f : pot / eps)) * kLog2e;
-      if (XY) (is_col ? hR : hC)[buf * kTok + idx] = hv;
-      else hR[buf * kTok + idx] = hv;
+    // the potentials become entries of the h vectors the other side reads (same side for the symmetric problems)
+    if (active) {
+      if (XY) {
+        if (part == 0) hR[buf * kTok + idx] = (logw + (step < 0 ? 0.f : pot_g * inv_eps)) * kLog2e;
+        if (part == 1) hC[(buf * 4 + (idx & 3)) * kHP + (idx >> 2)] = (logw + (step < 0 ? 0.f : pot_f * inv_eps)) * kLog2e;
+      } else if (part == 0) {
+        hR[buf * kTok + idx] = (logw + (step < 0 ? 0.f : pot_f * inv_eps)) * kLog2e;
+      }
     }
     __syncthreads();
-    const float c2 = kLog2e / eps;
-    Lse a{0.f, 1.f};
-    if (active) {
-      if (is_col) a = lse2_col(sC + idx, hC + buf * kTok, c2);
-      else a = lse2_row_part(sC + idx * LD, hR + buf * kTok, c2, k0, k1);
-    }
-    if (!XY) {   // the two halves of a row sit in adjacent lanes
-      Lse o;
-      o.m = __shfl_xor_sync(0xffffffffu, a.m, 1);
-      o.s = __shfl_xor_sync(0xffffffffu, a.s, 1);
-      a = lse_merge(a, o);
-    }
-    if (active) {
-      if (!is_col) { fin = a; c2_fin = c2; }
-      const float upd = -eps * kLn2 * (a.m + __log2f(a.s));
-      pot = (step < 0 || step == n) ? upd : 0.5f * (pot + upd);
+    const float c2 = kLog2e * inv_eps;
+    const Lse a = lse_merge4(lse2_row_part(sC + row * LD, hR + buf * kTok, c2, k0, k1));
+    fin = a; c2_fin = c2;
+    const float upd_f = -eps * kLn2 * (a.m + __log2f(a.s));
+    pot_f = (step < 0 || step == n) ? upd_f : 0.5f * (pot_f + upd_f);
+    if (XY) {
+      const Lse b = lse_merge4(lse2_col_part(sC + part * LD + row, hC + (buf * 4 + part) * kHP, c2));
+      const float upd_g = -eps * kLn2 * (b.m + __log2f(b.s));
+      pot_g = (step < 0 || step == n) ? upd_g : 0.5f * (pot_g + upd_g);
     }
   }
 
   // divergence partial: xy -> +(sum f_ba + sum g_ab)/N ; xx, yy -> -(sum f)/N
-  double acc = (active && half == 0) ? (double)pot : 0.0;
+  double acc = (active && part == 0) ? (double)pot_f + (XY ? (double)pot_g : 0.0) : 0.0;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -347,7 +379,7 @@ __global__ void __launch_bounds__(XY ? 2 * kRoleThreads : kSymThreads, 1) sinkho
     p.partials[pair * 3 + which] = (XY ? s : -s) / (double)kTok;
   }
   // transport plans of the last step (rows only): -P from C_xy, Q from C_xx
-  if (p.write_plans && active && !is_col && which != 2) {
+  if (p.write_plans && active && which != 2) {
     const int mat = XY ? 1 : 0;
     const size_t plane = (size_t)p.pairs * kTok * kLDP;
     __nv_bfloat16* hi = p.plans + ((size_t)mat * 2 * p.pairs + pair) * kTok * kLDP + (size_t)idx * kLDP;
@@ -513,10 +545,10 @@ int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const
     sp.pairs = pairs; sp.write_plans = want_grads;
     cudaFuncSetAttribute(sinkhorn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSinkSmem);
     cudaFuncSetAttribute(sinkhorn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSinkSmem);
-    sinkhorn_kernel<true><<<pairs, 2 * kRoleThreads, kSinkSmem, st>>>(sp);
+    sinkhorn_kernel<true><<<pairs, kSinkThreads, kSinkSmem, st>>>(sp);
     rc = check_launch("dkd_wass_sinkhorn_fwdbwd: sinkhorn xy");
     if (rc != DKD_OK) return rc;
-    sinkhorn_kernel<false><<<pairs * 2, kSymThreads, kSinkSmem, st>>>(sp);
+    sinkhorn_kernel<false><<<pairs * 2, kSinkThreads, kSinkSmem, st>>>(sp);
     rc = check_launch("dkd_wass_sinkhorn_fwdbwd: sinkhorn xx/yy");
     if (rc != DKD_OK) return rc;
     rc = launch_fold_partials(ws.partials, pairs * 3, scale, loss, st);

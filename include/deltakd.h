@@ -217,7 +217,9 @@ DKD_API int dkd_masked_generation_fwdbwd(const void* s, const void* t, const flo
  *
  * dkd_saliency_selfdiag_score — method 1: score[b,i] = mean_h softmax_j(q_i.k_j / sqrt(48))[i] over the n_tok
  *   patch tokens x[b, off + i, :] of x [B, T, D] (`dtype`); qk_w [2D, D], qk_b [2D] fp32 (q = first D outputs).
- *   The qk projection runs on tcgen05 (`precision`), the attention maps are never materialised.
+ *   Built for n_tok = 196.  Both contractions run on tcgen05: the qk projection (`precision`) writes q (pre-scaled) and
+ *   k as bf16 planes, and one 128 x 208 x 48 GEMM per (sample, head, query half) forms the logits in tensor memory,
+ *   where the epilogue reduces each row to its softmax diagonal — the attention maps are never materialised.
  * dkd_saliency_cls_score — methods 2 and 3: one query token per sample (xq + b*xq_stride, strides in elements)
  *   against n_keys key tokens (xk + b*xk_stride + j*D); separate q / k projections Wq,bq / Wk,bk ([D,D],[D], fp32;
  *   biases may be NULL).  query_is_key != 0 also counts the query token as key 0 of the softmax and drops its

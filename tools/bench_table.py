@@ -20,6 +20,8 @@ for path in sys.argv[1:]:
         par = r.get("parity") or {}
         cpu = r.get("cpu_baseline") or {}
         extra = f" mufu={rf['mufu_frac']:.3f}" if "mufu_frac" in rf else ""
+        if "eigensolve_us" in rf:
+            extra += f" eig={rf['eigensolve_us']:.0f}us/{max(rf['eigensolve_sweeps'])}sw"
         print(f"{r['workload']:40s} {r['ms_per_step'] * 1e3:10.1f} us/step  op {rf['kernel_us']:9.1f} us  {rf['bound']:6s} frac {rf['frac']:.3f}{extra}"
               f"  e2e {r['e2e']['ms_per_step'] * 1e3:9.1f} us  value {r['value']:.4g}  cpu {cpu.get('value', float('nan')):.4g}"
               f"  parity {par.get('rel_err', float('nan')):.1e}/{par.get('batch')}")
