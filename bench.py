@@ -192,8 +192,16 @@ class LogitKD(Workload):
         self.crit = DistillationLoss(call_base_loss(self.args), self.teacher, self.kind, self.alpha, self.tau)
         self.inputs = torch.zeros(self.B, 3, 2, 2, device=self.device)  # images feed only the (replayed) teacher
 
-    def to_device(self, hs):
-        d = hs.to(self.device, non_blocking=True)
+    def to_device(self, hs, slot=None):
+        """slot = None: fresh device tensors; slot = k: copy into the persistent device buffer k (the prefetching e2e loop)."""
+        if slot is None:
+            d = hs.to(self.device, non_blocking=True)
+        else:
+            slots = self.__dict__.setdefault("_slots", {})
+            if slot not in slots or slots[slot].shape != hs.shape:
+                slots[slot] = torch.empty_like(hs, device=self.device)
+            d = slots[slot]
+            d.copy_(hs, non_blocking=True)
         return d[0].requires_grad_(True), d[1].requires_grad_(True), d[2], d[3]
 
     def h2d_bytes(self):
@@ -304,9 +312,22 @@ class FeatureKD(Workload):
         self.crit = DistillationLoss(call_base_loss(self.args), self.teacher, self.kind, 0.1, 3.0)
         self.inputs = torch.zeros(self.B, 3, 2, 2, device=self.device)
 
-    def to_device(self, hs):
-        mv = lambda x: None if x is None else x.to(self.device, non_blocking=True)
-        d = dict(s=[mv(x) for x in hs["s"]], t=[mv(x) for x in hs["t"]], z=mv(hs["z"]), y=mv(hs["y"]), noise=mv(hs["noise"]))
+    def to_device(self, hs, slot=None):
+        if slot is None:
+            mv = lambda key, x: None if x is None else x.to(self.device, non_blocking=True)
+        else:
+            bufs = self.__dict__.setdefault("_slots", {}).setdefault(slot, {})
+
+            def mv(key, x):
+                if x is None:
+                    return None
+                b = bufs.get(key)
+                if b is None or b.shape != x.shape:
+                    b = bufs[key] = torch.empty_like(x, device=self.device)
+                b.copy_(x, non_blocking=True)
+                return b.detach()
+        d = dict(s=[mv(("s", i), x) for i, x in enumerate(hs["s"])], t=[mv(("t", i), x) for i, x in enumerate(hs["t"])],
+                 z=mv("z", hs["z"]), y=mv("y", hs["y"]), noise=mv("noise", hs["noise"]))
         for x in d["s"]:
             if x is not None:
                 x.requires_grad_(True)
@@ -645,8 +666,15 @@ class DeiTKDStep(Workload):
             self._graph = g
             torch.cuda.synchronize()
 
-    def to_device(self, hs):
-        return tuple(t.to(self.device, non_blocking=True) for t in hs)
+    def to_device(self, hs, slot=None):
+        if slot is None:
+            return tuple(t.to(self.device, non_blocking=True) for t in hs)
+        bufs = self.__dict__.setdefault("_slots", {})
+        if slot not in bufs:
+            bufs[slot] = tuple(torch.empty_like(t, device=self.device) for t in hs)
+        for b, t in zip(bufs[slot], hs):
+            b.copy_(t, non_blocking=True)
+        return bufs[slot]
 
     def h2d_bytes(self):
         return self.bytes_per_set()
@@ -934,6 +962,7 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
         k_ms = ms / K
 
     # ---- end to end through the public API with host buffers
+    # (a) serial: copy in, step, read the loss back (a host synchronisation) — every step waits for the previous one
     for i in range(W):
         w.step(w.to_device(host[i % nsets])).item()
     barrier()
@@ -946,7 +975,83 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
     e3.record()
     torch.cuda.synchronize()
     windows.append((t0, time.time()))
-    ms_e2e = allmax([e2.elapsed_time(e3)])[0]
+    ms_e2e_serial = allmax([e2.elapsed_time(e3)])[0]
+    # (b) the way an input pipeline feeds a training loop: the same K host->device copies and K loss read-backs, all inside
+    # the timed region, but the copy of step i+1 runs on a second stream while step i computes, and the losses land in pinned
+    # memory that is read after the one synchronisation at the end (possible because the loss path never syncs the host)
+    main, copy_stream = torch.cuda.current_stream(), torch.cuda.Stream()
+    loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+    done = [None, None]        # per device input slot: the step that last read it has finished
+
+    def fetch(i):
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            if done[slot] is not None:
+                copy_stream.wait_event(done[slot])
+            ds_ = w.to_device(host[i % nsets], slot=slot)
+            ev_ = torch.cuda.Event()
+            ev_.record(copy_stream)
+        return ds_, ev_, slot
+
+    for i in range(2):         # allocate the two device slots outside the timed region
+        fetch(i)
+    barrier()
+    torch.cuda.synchronize()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e4.record()
+    nxt = fetch(W)
+    for i in range(K):
+        ds_, ev_, slot = nxt
+        main.wait_event(ev_)
+        if i + 1 < K:
+            nxt = fetch(W + i + 1)
+        loss_host[i].copy_(w.step(ds_).detach(), non_blocking=True)
+        done[slot] = torch.cuda.Event()
+        done[slot].record(main)
+    e5.record()
+    torch.cuda.synchronize()
+    windows.append((t0, time.time()))
+    if not bool(torch.isfinite(loss_host).all()):
+        raise RuntimeError(f"{w.name}: non-finite loss in the pipelined end-to-end loop")
+    ms_e2e_prefetch = allmax([e4.elapsed_time(e5)])[0]
+    del nxt
+    # (c) launch-bound steps: one CUDA graph per step = the H2D copies of that step's pinned host inputs + the public-API
+    # forward / backward + the D2H copy of the loss; the host launches it and WAITS for the loss before the next step
+    ms_e2e_graph = None
+    if getattr(w, "graphable", True):
+        ng = min(nsets, 4)
+        loss_pin = torch.zeros(ng, dtype=torch.float32).pin_memory()
+
+        def one(j):
+            def fn(_):
+                loss_pin[j].copy_(w.step(w.to_device(host[(W + j) % nsets], slot="graph")).detach(), non_blocking=True)
+            return fn
+        graphs = [_graph_of(one(j), 1)[0] for j in range(ng)]
+        for j in range(min(W, ng)):
+            graphs[j].replay()
+        barrier()
+        torch.cuda.synchronize()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e6.record()
+        acc = 0.0
+        for i in range(K):
+            graphs[i % ng].replay()
+            main.synchronize()
+            acc += float(loss_pin[i % ng])
+        e7.record()
+        torch.cuda.synchronize()
+        windows.append((t0, time.time()))
+        if acc != acc:
+            raise RuntimeError(f"{w.name}: non-finite loss in the graph end-to-end loop")
+        ms_e2e_graph = allmax([e6.elapsed_time(e7)])[0]
+        del graphs
+    e2e_modes = {"serial": ms_e2e_serial, "prefetch": ms_e2e_prefetch}
+    if ms_e2e_graph is not None:
+        e2e_modes["graph"] = ms_e2e_graph
+    e2e_best = min(e2e_modes, key=e2e_modes.get)
+    ms_e2e = e2e_modes[e2e_best]
 
     if w.bound == "hbm":
         ach, peak, unit, alg = w.algorithmic_bytes() / (k_ms * 1e-3) / 1e9, pk["hbm"], "GB/s", w.algorithmic_bytes()
@@ -959,7 +1064,16 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
         "l2": (f"{nsets} rotating input sets ({nsets * w.bytes_per_set() / 2**20:.0f} MiB > 126 MiB L2)" if nsets > 1
                else f"one input set of {w.bytes_per_set() / 2**20:.0f} MiB (> 126 MiB L2)"),
         "e2e": {"value": world * w.B * K / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": w.h2d_bytes(),
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K,
+                "mode": e2e_best,
+                "modes": {"serial": "copy in, DistillationLoss forward + backward, loss.item() (host sync) every step",
+                          "prefetch": "the same calls; the H2D copy of step i+1 runs on a second stream while step i computes, losses land in "
+                                      "pinned memory and are read after the one synchronize at the end",
+                          "graph": "one CUDA graph per step (H2D copies of the pinned inputs + the captured public-API forward / backward + D2H "
+                                   "copy of the loss); the host waits for every step's loss"},
+                "ms_per_step_by_mode": {k: v / K for k, v in e2e_modes.items()},
+                "note": "value = the best of the modes above; in every mode each step's H2D input copy and D2H loss copy are inside the timed region",
+                "serial_ms_per_step": ms_e2e_serial / K},
         "gpu_launches": int(launches),
         "roofline": {"bound": w.bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                      "traffic": NCU_TRAFFIC.get(w.name, {}).get("bytes"), "traffic_source": NCU_TRAFFIC.get(w.name, {}).get("source"),

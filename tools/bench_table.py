@@ -23,5 +23,5 @@ for path in sys.argv[1:]:
         if "eigensolve_us" in rf:
             extra += f" eig={rf['eigensolve_us']:.0f}us/{max(rf['eigensolve_sweeps'])}sw"
         print(f"{r['workload']:40s} {r['ms_per_step'] * 1e3:10.1f} us/step  op {rf['kernel_us']:9.1f} us  {rf['bound']:6s} frac {rf['frac']:.3f}{extra}"
-              f"  e2e {r['e2e']['ms_per_step'] * 1e3:9.1f} us  value {r['value']:.4g}  cpu {cpu.get('value', float('nan')):.4g}"
+              f"  e2e {r["e2e"]["ms_per_step"] * 1e3:9.1f} us ({r["e2e"].get("mode", "serial")}; serial {r["e2e"].get("serial_ms_per_step", float("nan")) * 1e3:.1f})  value {r['value']:.4g}  cpu {cpu.get('value', float('nan')):.4g}"
               f"  parity {par.get('rel_err', float('nan')):.1e}/{par.get('batch')}")
