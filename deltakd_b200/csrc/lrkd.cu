@@ -679,42 +679,43 @@ struct SelectParams {
   int k, BN, Ds, P;
 };
 
-// 4a. one CTA per layer: column norms (= eigenvalues), the sign convention and the descending order.  One warp per
-// column (coalesced 256-byte reads); the largest-magnitude component is found with its index so that ties resolve to
-// the first row, as a sequential scan would.
+// 4a. column norms (= eigenvalues) and the sign convention: one warp per column (coalesced 256-byte reads), 8 columns per
+// CTA so that the columns' global-memory round trips overlap; the largest-magnitude component is found with its index
+// so that ties resolve to the first row, as a sequential scan would.  Then one CTA per layer ranks the norms.
+__global__ void __launch_bounds__(256) eig_norm_kernel(SelectParams p) {
+  constexpr int n = kN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int layer = blockIdx.x / (n / 8), j = (blockIdx.x % (n / 8)) * 8 + warp;
+  const double* col = p.W + (size_t)layer * n * n + (size_t)j * n;
+  // (the magnitude is tracked in its own variable: with `fabs(v) > fabs(big)` nvcc 12.9 drops the fabs of `big` in the
+  // second unrolled comparison — DSETP.GT |v1|, v0 in the SASS — and a negative first element loses)
+  double a = 0.0, big = 0.0, mag = 0.0;
+  int bi = n;
+#pragma unroll
+  for (int k = 0; k < n / 32; ++k) {
+    const double v = col[lane + 32 * k], av = fabs(v);
+    a = fma(v, v, a);
+    if (av > mag) { mag = av; big = v; bi = lane + 32 * k; }
+  }
+  a = warp_sum_d(a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double om = __shfl_xor_sync(0xffffffffu, mag, o);
+    const double ob = __shfl_xor_sync(0xffffffffu, big, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (om > mag || (om == mag && oi < bi)) { mag = om; big = ob; bi = oi; }
+  }
+  if (lane == 0) {
+    p.lam[layer * n + j] = sqrt(a);
+    p.sgn[layer * n + j] = big < 0.0 ? -1.f : 1.f;   // sign convention: largest-magnitude component positive
+  }
+}
 __global__ void __launch_bounds__(kN) eig_rank_kernel(SelectParams p) {
   constexpr int n = kN;
   __shared__ double lam[n];
-  const int layer = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double* W = p.W + (size_t)layer * n * n;
-  for (int j = warp; j < n; j += n / 32) {
-    const double* col = W + (size_t)j * n;
-    // (the magnitude is tracked in its own variable: with `fabs(v) > fabs(big)` nvcc 12.9 drops the fabs of `big` in the
-    // second unrolled comparison — DSETP.GT |v1|, v0 in the SASS — and a negative first element loses)
-    double a = 0.0, big = 0.0, mag = 0.0;
-    int bi = n;
-#pragma unroll
-    for (int k = 0; k < n / 32; ++k) {
-      const double v = col[lane + 32 * k], av = fabs(v);
-      a = fma(v, v, a);
-      if (av > mag) { mag = av; big = v; bi = lane + 32 * k; }
-    }
-    a = warp_sum_d(a);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double om = __shfl_xor_sync(0xffffffffu, mag, o);
-      const double ob = __shfl_xor_sync(0xffffffffu, big, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (om > mag || (om == mag && oi < bi)) { mag = om; big = ob; bi = oi; }
-    }
-    if (lane == 0) {
-      lam[j] = sqrt(a);
-      p.lam[layer * n + j] = sqrt(a);
-      p.sgn[layer * n + j] = big < 0.0 ? -1.f : 1.f;   // sign convention: largest-magnitude component positive
-    }
-  }
+  const int layer = blockIdx.x, j = threadIdx.x;
+  lam[j] = p.lam[layer * n + j];
   __syncthreads();
-  const int j = threadIdx.x;
   const double v = lam[j];
   int rank = 0;
   for (int i = 0; i < n; ++i) rank += (lam[i] > v) || (lam[i] == v && i < j);
@@ -969,6 +970,9 @@ int dkd_lrkd_fwdbwd(int n_layers, const void* const* s, const void* const* t, co
     sp.lam = ws.gsum;
     sp.order = reinterpret_cast<int*>(ws.gsum + (size_t)kMaxLayers * kN);
     sp.sgn = reinterpret_cast<float*>(sp.order + (size_t)kMaxLayers * kN);
+    eig_norm_kernel<<<n_layers * (kN / 8), 256, 0, st>>>(sp);
+    rc = check_launch("dkd_lrkd_fwdbwd: eigenvalues");
+    if (rc != DKD_OK) return rc;
     eig_rank_kernel<<<n_layers, kN, 0, st>>>(sp);
     rc = check_launch("dkd_lrkd_fwdbwd: eigenvalue ranking");
     if (rc != DKD_OK) return rc;
