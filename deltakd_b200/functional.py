@@ -9,6 +9,7 @@ rescales them on the device when the incoming grad is not 1
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -259,6 +260,18 @@ def _scratch(device: torch.device, tag: str, nbytes: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- hidden-state matching
+_LAYER_STREAMS = os.environ.get("DKD_LAYER_STREAMS", "1") != "0"
+_SIDE_STREAMS: dict = {}
+
+
+def _side_streams(device: torch.device, n: int):
+    """n persistent side streams of `device` (the per-layer calls of the multi-layer feature losses fork onto them)."""
+    lst = _SIDE_STREAMS.setdefault(device.index if device.index is not None else torch.cuda.current_device(), [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(device=device))
+    return lst[:n]
+
+
 class _AlignMseLayers(torch.autograd.Function):
     """sum_i scale * || Linear_i(s_i[:, 1:]) - t_i[:, 2:] ||^2 over the selected layers (fused fwd+bwd)."""
 
@@ -269,27 +282,44 @@ class _AlignMseLayers(torch.autograd.Function):
         w_list = tensors[2 * n_layers:3 * n_layers]
         b_list = tensors[3 * n_layers:4 * n_layers]
         dev = s_list[0].device
-        loss = torch.zeros((), dtype=torch.float32, device=dev)
-        grads = []
+        # The layers are independent: each runs on its own stream (own scratch: the scratch cache is keyed by stream), so the
+        # last, partly filled wave of one layer's persistent kernels (784 row tiles on 148 SMs = 5.3 waves; 512 Sinkhorn CTAs
+        # = 3.5 waves) overlaps the next layer's first kernels instead of idling two thirds of the SMs.  Outputs are
+        # allocated on the calling stream, which forks before the first launch and joins after the last.
+        multi = n_layers > 1 and _LAYER_STREAMS
+        loss_parts = torch.zeros(n_layers if multi else 1, dtype=torch.float32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        sides = _side_streams(dev, n_layers - 1) if multi else []
+        grads, outs = [], []
         for i in range(n_layers):
-            s, t, W, b = s_list[i], t_list[i], w_list[i], b_list[i]
-            B, Ts, Ds = s.shape
-            _, Tt, Dt = t.shape
-            n_tok = Ts - s_off
-            dt = _dtype_code(s)
-            prec = _precision_for(s)
+            s, W, b = s_list[i], w_list[i], b_list[i]
             need_s = ctx.needs_input_grad[5 + i]
             need_w = ctx.needs_input_grad[5 + 2 * n_layers + i]
             need_b = b is not None and ctx.needs_input_grad[5 + 3 * n_layers + i]
             g_s = torch.empty_like(s) if need_s else None
             g_W = torch.empty_like(W) if (need_w or need_b) else None
             g_b = torch.empty_like(b) if need_b else None
-            nbytes = getattr(_lib.lib, entry + "_workspace_bytes")(B, n_tok, Ds, Dt, prec)
-            ws = _scratch(dev, entry, nbytes)
-            _lib.call(entry + "_fwdbwd", _ptr(s), _ptr(t), _ptr(W), _ptr(b), B, Ts, s_off, Tt, t_off, n_tok,
-                      Ds, Dt, dt, prec, float(scale), _ptr(g_s), _ptr(g_W), _ptr(g_b), _ptr(loss), _ptr(ws),
-                      ws.numel(), _stream())
+            outs.append((g_s, g_W, g_b))
             grads.append((g_s, g_W if need_w else None, g_b))
+        for st in sides:
+            st.wait_stream(main)
+        for i in reversed(range(n_layers)):   # side streams first, the calling stream (layer 0) last
+            s, t, W, b = s_list[i], t_list[i], w_list[i], b_list[i]
+            B, Ts, Ds = s.shape
+            _, Tt, Dt = t.shape
+            n_tok = Ts - s_off
+            dt = _dtype_code(s)
+            prec = _precision_for(s)
+            g_s, g_W, g_b = outs[i]
+            nbytes = getattr(_lib.lib, entry + "_workspace_bytes")(B, n_tok, Ds, Dt, prec)
+            with torch.cuda.stream(main if (i == 0 or not multi) else sides[i - 1]):
+                ws = _scratch(dev, entry, nbytes)
+                _lib.call(entry + "_fwdbwd", _ptr(s), _ptr(t), _ptr(W), _ptr(b), B, Ts, s_off, Tt, t_off, n_tok,
+                          Ds, Dt, dt, prec, float(scale), _ptr(g_s), _ptr(g_W), _ptr(g_b),
+                          loss_parts.data_ptr() + (4 * i if multi else 0), _ptr(ws), ws.numel(), _stream())
+        for st in sides:
+            main.wait_stream(st)
+        loss = loss_parts.sum() if multi else loss_parts[0]
         ctx.grads = grads
         ctx.n_layers = n_layers
         return loss
