@@ -39,7 +39,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// ------------------------------------------------------------------ 4. norms, diameter, eps ladder
+// ------------------------------------------------------------------ 4. norms, diameter, eps ladder (one kernel, one pass)
 struct PrepParams {
   const float* A;     // [B*196, 384] aligned student
   const void* t;      // teacher [B, Tt, 384]
@@ -54,24 +54,58 @@ __device__ __forceinline__ float ld_t(const void* t, int64_t idx, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(t)[idx]) : reinterpret_cast<const float*>(t)[idx];
 }
 
-// one CTA per pair, thread = coordinate: bounding box of x u y -> diameter -> eps list (geomloss epsilon_schedule)
+// One CTA per pair, ONE pass over the pair's 196 aligned-student rows and 196 teacher rows: a warp takes every 12th row,
+// a lane 12 of its 384 coordinates (three float4) — square norms of the rows (lane-local sums in a fixed order, then a warp
+// sum) and, per coordinate, the bounding box of x u y -> diameter -> eps list (geomloss epsilon_schedule).
 __global__ void __launch_bounds__(kD) sinkhorn_prep_kernel(PrepParams p) {
-  const int b = blockIdx.x, d = threadIdx.x;
-  float mn = INFINITY, mx = -INFINITY;
-  for (int i = 0; i < kTok; ++i) {
-    const float a = p.A[((int64_t)b * kTok + i) * kD + d];
-    const float y = ld_t(p.t, ((int64_t)b * p.Tt + p.t_off + i) * kD + d, p.t_is_bf16);
-    mn = fminf(mn, fminf(a, y));
-    mx = fmaxf(mx, fmaxf(a, y));
+  constexpr int kWarps = kD / 32;
+  __shared__ float s_mn[kWarps][kD], s_mx[kWarps][kD];
+  __shared__ double red[kWarps];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mn[12], mx[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+  for (int i = warp; i < kTok; i += kWarps) {
+    const int64_t row = (int64_t)b * kTok + i;
+    const int64_t trow = ((int64_t)b * p.Tt + p.t_off + i) * kD;
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane * 4 + 128 * k;
+      float a[4], y[4];
+      Vec<float, 4>::load(p.A + row * kD + c, a);
+      if (p.t_is_bf16) Vec<__nv_bfloat16, 4>::load(reinterpret_cast<const __nv_bfloat16*>(p.t) + trow + c, y);
+      else Vec<float, 4>::load(reinterpret_cast<const float*>(p.t) + trow + c, y);
+      sx += a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3];
+      sy += y[0] * y[0] + y[1] * y[1] + y[2] * y[2] + y[3] * y[3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mn[4 * k + q] = fminf(mn[4 * k + q], fminf(a[q], y[q]));
+        mx[4 * k + q] = fmaxf(mx[4 * k + q], fmaxf(a[q], y[q]));
+      }
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy);
+    if (lane == 0) { p.nx[row] = sx; p.ny[row] = sy; }
   }
-  __shared__ double red[kD / 32];
-  double r = (double)(mx - mn) * (double)(mx - mn);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s_mn[warp][lane * 4 + 128 * k + q] = mn[4 * k + q];
+      s_mx[warp][lane * 4 + 128 * k + q] = mx[4 * k + q];
+    }
+  __syncthreads();
+  const int d = threadIdx.x;
+  float lo = s_mn[0][d], hi = s_mx[0][d];
+#pragma unroll
+  for (int w = 1; w < kWarps; ++w) { lo = fminf(lo, s_mn[w][d]); hi = fmaxf(hi, s_mx[w][d]); }
+  double r = (double)(hi - lo) * (double)(hi - lo);
   r = warp_sum(r);
   if ((d & 31) == 0) red[d >> 5] = r;
   __syncthreads();
   if (d == 0) {
     double s = 0.0;
-    for (int w = 0; w < kD / 32; ++w) s += red[w];
+    for (int w = 0; w < kWarps; ++w) s += red[w];
     const double diam = (double)(float)sqrt(s);   // torch: fp32 .norm().item()
     float* e = p.eps + (size_t)b * kMaxEps;
     const double start = 2.0 * log(diam), stop = 2.0 * log((double)p.blur), step = 2.0 * log((double)p.scaling);
@@ -83,26 +117,6 @@ __global__ void __launch_bounds__(kD) sinkhorn_prep_kernel(PrepParams p) {
     e[1 + n] = p.blur * p.blur;
     p.n_eps[b] = n + 2;
   }
-}
-
-// warp per row: square norms of the aligned student rows and of the teacher rows
-__global__ void __launch_bounds__(256) sinkhorn_norms_kernel(PrepParams p, int64_t M) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int64_t b = row / kTok, i = row - b * kTok;
-  float sx = 0.f, sy = 0.f;
-  for (int c = lane * 4; c < kD; c += 128) {
-    float v[4];
-    Vec<float, 4>::load(p.A + row * kD + c, v);
-    sx += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
-    const int64_t toff = (b * p.Tt + p.t_off + i) * kD + c;
-    if (p.t_is_bf16) Vec<__nv_bfloat16, 4>::load(reinterpret_cast<const __nv_bfloat16*>(p.t) + toff, v);
-    else Vec<float, 4>::load(reinterpret_cast<const float*>(p.t) + toff, v);
-    sy += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
-  }
-  sx = warp_sum(sx); sy = warp_sum(sy);
-  if (lane == 0) { p.nx[row] = sx; p.ny[row] = sy; }
 }
 
 // ------------------------------------------------------------------ 5. cost matrices (gemm_tn policies)
@@ -512,10 +526,7 @@ int dkd_wass_sinkhorn_fwdbwd(const void* s, const void* t, const float* W, const
   pp.A = ws.A; pp.t = t; pp.nx = ws.nx; pp.ny = ws.ny; pp.eps = ws.eps; pp.n_eps = ws.n_eps;
   pp.Tt = Tt; pp.t_off = t_off; pp.t_is_bf16 = dtype == DKD_BF16; pp.blur = 0.05f; pp.scaling = 0.5f;
   sinkhorn_prep_kernel<<<pairs, kD, 0, st>>>(pp);
-  rc = check_launch("dkd_wass_sinkhorn_fwdbwd: eps ladder");
-  if (rc != DKD_OK) return rc;
-  sinkhorn_norms_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(pp, M);
-  rc = check_launch("dkd_wass_sinkhorn_fwdbwd: norms");
+  rc = check_launch("dkd_wass_sinkhorn_fwdbwd: norms, eps ladder");
   if (rc != DKD_OK) return rc;
 
   {  // 5. cost matrices
