@@ -90,3 +90,56 @@ def test_two_streams_do_not_share_scratch():
     assert all(o.item() == want for o in outs)
     keys = [k for k in Fn._WS if k[2] == "logit_kd"]
     assert len({k[1] for k in keys}) >= 3   # default stream + the two side streams
+
+
+@pytest.mark.parametrize("entry", ["dkd_align_mse", "dkd_wass_l1"])
+def test_layers_on_their_own_streams_give_the_same_result(entry, monkeypatch):
+    """The multi-layer feature losses fork every layer onto its own stream (functional._LAYER_STREAMS): same kernels, same
+    per-layer scratch sizes — the feature gradients must be bit-identical to the single-stream order, the loss and the
+    (atomically reduced) weight gradients equal up to the order of the adds; the fork / join must also survive a CUDA-graph capture and two replays."""
+    from deltakd_b200 import functional as Fn
+    B = 5
+    s_feats, t_feats = synth.make_features(B, 21, layers=[0, 1, 2])
+    lins = [torch.nn.Linear(192, 384).cuda() for _ in range(3)]
+
+    def run(multi):
+        monkeypatch.setattr(Fn, "_LAYER_STREAMS", multi)
+        s = [s_feats[i].cuda().requires_grad_(True) for i in range(3)]
+        t = [t_feats[i].cuda() for i in range(3)]
+        for lin in lins:
+            lin.zero_grad(set_to_none=True)
+        loss = Fn.align_mse_layers_loss(s, t, lins, scale=1e-3, _entry=entry)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.item(), [x.grad.clone() for x in s], [lin.weight.grad.clone() for lin in lins]
+
+    l1, gs1, gw1 = run(True)
+    l0, gs0, gw0 = run(False)
+    assert abs(l1 - l0) <= 1e-6 * abs(l0)
+    for a, b in zip(gs1, gs0):
+        assert torch.equal(a, b)
+    for a, b in zip(gw1, gw0):   # split-K weight gradients are reduced with fp32 atomics: equal up to the order of the adds
+        assert rel_err(a, b) < 1e-5
+
+    # under capture: fork / join become graph dependencies
+    monkeypatch.setattr(Fn, "_LAYER_STREAMS", True)
+    s = [s_feats[i].cuda().requires_grad_(True) for i in range(3)]
+    t = [t_feats[i].cuda() for i in range(3)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        Fn.align_mse_layers_loss(s, t, lins, scale=1e-3, _entry=entry).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for x in s:
+        x.grad = None
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        loss = Fn.align_mse_layers_loss(s, t, lins, scale=1e-3, _entry=entry)
+        loss.backward()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - l0) <= 1e-6 * abs(l0)
+    for a, b in zip([x.grad for x in s], gs0):
+        assert torch.equal(a, b)
