@@ -548,6 +548,7 @@ class CurKDEarlyBf16(CurKDEarly):
     name = "curkd_early_3layers_b512_bf16"
     dtype = "bf16"
     tdtype = torch.bfloat16
+    bound = "tensor"   # AI = 288 FLOP/B with bf16 I/O, above the ridge (214): the tensor pipe bounds it (94.9 us vs 70.6 us of HBM time)
 
 
 class MGDBf16(MGD):
@@ -1085,6 +1086,12 @@ def measure(w: Workload, K: int, W: int, world: int, barrier, allmax, pk, with_c
                          if getattr(w, "_graph", None) is not None else "eager steps (optimizer + DDP inside), CUDA events, max over ranks")
     if w.bound == "hbm" and w.algorithmic_flops():
         res["roofline"]["algorithmic_flops"] = w.algorithmic_flops()
+    try:   # both fractions where both algorithmic quantities are defined ("report both")
+        res["roofline"]["frac_hbm"] = w.algorithmic_bytes() / (k_ms * 1e-3) / 1e9 / pk["hbm"]
+        if w.algorithmic_flops():
+            res["roofline"]["frac_tensor"] = w.algorithmic_flops() / (k_ms * 1e-3) / 1e12 / pk["bf16_sus"]
+    except Exception:
+        pass
     if hasattr(w, "extra_roofline"):
         res["roofline"].update(w.extra_roofline(k_ms))
     if hasattr(w, "extra_info"):
